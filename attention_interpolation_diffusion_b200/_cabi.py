@@ -1,0 +1,228 @@
+"""ctypes binding of libpaid_attn.so (include/paid_attn.h).
+
+PyTorch is used for device memory and streams only: every call passes raw device
+pointers (``tensor.data_ptr()``) and the current ``cudaStream_t``.  There is no
+CPU or PyTorch fallback: if the library is missing or a call fails, a
+``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpaid_attn.so")
+
+PAID_OK, PAID_EINVAL, PAID_EUNSUPPORTED, PAID_ECUDA, PAID_EWORKSPACE = 0, -1, -2, -3, -4
+PAID_F16, PAID_BF16 = 0, 1
+PAID_PLAIN, PAID_OUTER, PAID_INNER = 0, 1, 2
+FLAG_GENERIC_KERNELS = 1
+MODES = {"plain": PAID_PLAIN, "outer": PAID_OUTER, "inner": PAID_INNER}
+
+EXPORTS = [
+    "paid_attn_abi_version", "paid_attn_workspace_bytes", "paid_attn_core_workspace_bytes", "paid_attn_forward",
+    "paid_attn_core", "paid_attn_project_endpoints", "paid_linear", "paid_attn_last_error",
+    "paid_attn_launch_count", "paid_attn_last_kernel",
+]
+
+
+class PaidAttnParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("flags", C.c_uint32),
+        ("dtype", C.c_int32), ("mode", C.c_int32), ("fused", C.c_int32),
+        ("N", C.c_int32), ("S", C.c_int32), ("L", C.c_int32), ("C", C.c_int32), ("Cc", C.c_int32),
+        ("heads", C.c_int32), ("scale", C.c_float),
+        ("begin_frame", C.c_int32), ("end_frame", C.c_int32),
+        ("x", C.c_void_p), ("ctx", C.c_void_p), ("wq", C.c_void_p), ("wk", C.c_void_p), ("wv", C.c_void_p),
+        ("wo", C.c_void_p), ("bo", C.c_void_p), ("coef", C.c_void_p), ("kv_ext", C.c_void_p),
+        ("y", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
+    ]
+
+
+class PaidCoreParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("flags", C.c_uint32),
+        ("dtype", C.c_int32), ("mode", C.c_int32), ("fused", C.c_int32),
+        ("N", C.c_int32), ("S", C.c_int32), ("L", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
+        ("scale", C.c_float), ("begin_frame", C.c_int32), ("end_frame", C.c_int32),
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("kv_ext", C.c_void_p), ("coef", C.c_void_p),
+        ("out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
+    ]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load the in-tree shared library (built by ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.paid_attn_abi_version.restype = C.c_int
+    lib.paid_attn_workspace_bytes.restype = C.c_uint64
+    lib.paid_attn_workspace_bytes.argtypes = [C.POINTER(PaidAttnParams)]
+    lib.paid_attn_core_workspace_bytes.restype = C.c_uint64
+    lib.paid_attn_core_workspace_bytes.argtypes = [C.POINTER(PaidCoreParams)]
+    lib.paid_attn_forward.restype = C.c_int
+    lib.paid_attn_forward.argtypes = [C.POINTER(PaidAttnParams), C.c_void_p]
+    lib.paid_attn_core.restype = C.c_int
+    lib.paid_attn_core.argtypes = [C.POINTER(PaidCoreParams), C.c_void_p]
+    lib.paid_attn_project_endpoints.restype = C.c_int
+    lib.paid_attn_project_endpoints.argtypes = [C.POINTER(PaidAttnParams), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.paid_linear.restype = C.c_int
+    lib.paid_linear.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                C.c_int32, C.c_uint32, C.c_void_p]
+    lib.paid_attn_last_error.restype = C.c_char_p
+    lib.paid_attn_launch_count.restype = C.c_uint64
+    lib.paid_attn_last_kernel.restype = C.c_char_p
+    if lib.paid_attn_abi_version() != 1:
+        raise RuntimeError("libpaid_attn.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load_library().paid_attn_last_error().decode()
+
+
+def last_kernel() -> str:
+    return load_library().paid_attn_last_kernel().decode()
+
+
+def launch_count() -> int:
+    return int(load_library().paid_attn_launch_count())
+
+
+def _check(status: int, what: str):
+    if status != PAID_OK:
+        raise RuntimeError(f"{what} failed with status {status}: {last_error()}")
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float16:
+        return PAID_F16
+    if t.dtype == torch.bfloat16:
+        return PAID_BF16
+    raise NotImplementedError(f"libpaid_attn computes in fp16/bf16 (fp32 accumulate); got {t.dtype}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _dev_check(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("libpaid_attn needs CUDA tensors; there is no CPU path")
+        if not t.is_contiguous():
+            raise RuntimeError("libpaid_attn needs contiguous tensors")
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+_workspaces: dict = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """One growing scratch buffer per device; calls are stream-ordered so layers can share it."""
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+def make_params(x, ctx, wq, wk, wv, wo, bo, coef, heads: int, mode: int, fused: bool, scale: Optional[float] = None,
+                begin_frame: Optional[int] = None, end_frame: Optional[int] = None, kv_ext=None, flags: int = 0,
+                y=None) -> PaidAttnParams:
+    N, S, Cdim = x.shape
+    L, Cc = (S, Cdim) if ctx is None else (ctx.shape[1], ctx.shape[2])
+    p = PaidAttnParams()
+    p.struct_size = C.sizeof(PaidAttnParams)
+    p.flags = flags
+    p.dtype, p.mode, p.fused = _dtype_code(x), mode, int(bool(fused))
+    p.N, p.S, p.L, p.C, p.Cc, p.heads = N, S, L, Cdim, Cc, heads
+    p.scale = float((Cdim // heads) ** -0.5 if scale is None else scale)
+    p.begin_frame = 0 if begin_frame is None else begin_frame
+    p.end_frame = N - 1 if end_frame is None else end_frame
+    p.x, p.ctx, p.wq, p.wk, p.wv, p.wo, p.bo = map(_ptr, (x, ctx, wq, wk, wv, wo, bo))
+    p.coef, p.kv_ext, p.y = _ptr(coef), _ptr(kv_ext), _ptr(y)
+    return p
+
+
+def attn_forward(x, ctx, wq, wk, wv, wo, bo, coef, heads: int, mode: int, fused: bool, scale=None,
+                 begin_frame=None, end_frame=None, kv_ext=None, flags: int = 0, out=None) -> torch.Tensor:
+    """One processor call through ``paid_attn_forward``.  Tensors: x (N,S,C), ctx None|(N,L,Cc), weights as in
+    nn.Linear, coef fp32 (N,) on the device (None for plain mode)."""
+    lib = load_library()
+    _dev_check(x, ctx, wq, wk, wv, wo, bo, coef, kv_ext)
+    for t in (ctx, wq, wk, wv, wo, bo, kv_ext):
+        if t is not None and t.dtype != x.dtype:
+            raise RuntimeError("all tensors of a call must share one dtype")
+    if coef is not None and coef.dtype != torch.float32:
+        raise RuntimeError("coef must be fp32")
+    y = torch.empty_like(x) if out is None else out
+    p = make_params(x, ctx, wq, wk, wv, wo, bo, coef, heads, mode, fused, scale, begin_frame, end_frame, kv_ext, flags, y)
+    need = lib.paid_attn_workspace_bytes(C.byref(p))
+    if need == 0:
+        raise RuntimeError(f"paid_attn_workspace_bytes rejected the parameters: {last_error()}")
+    ws = _workspace(x.device, int(need))
+    p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    _check(lib.paid_attn_forward(C.byref(p), _stream(x)), "paid_attn_forward")
+    return y
+
+
+def project_endpoints(x, ctx, wk, wv, heads: int, local_frame: int, k_out: torch.Tensor, v_out: torch.Tensor,
+                      flags: int = 0):
+    lib = load_library()
+    _dev_check(x, ctx, wk, wv, k_out, v_out)
+    p = make_params(x, ctx, None, wk, wv, None, None, None, heads, PAID_PLAIN, False, flags=flags)
+    _check(lib.paid_attn_project_endpoints(C.byref(p), local_frame, k_out.data_ptr(), v_out.data_ptr(), _stream(x)),
+           "paid_attn_project_endpoints")
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
+    lib = load_library()
+    _dev_check(x, w, bias)
+    K = x.shape[-1]
+    M = x.numel() // K
+    y = torch.empty(*x.shape[:-1], w.shape[0], dtype=x.dtype, device=x.device)
+    _check(lib.paid_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), M, w.shape[0], K, _dtype_code(x),
+                           flags, _stream(x)), "paid_linear")
+    return y
+
+
+def attn_core(q, k, v, coef, heads: int, mode: int, fused: bool, scale=None, begin_frame=None, end_frame=None,
+              kv_ext=None, flags: int = 0) -> torch.Tensor:
+    """Attention on projected tensors through ``paid_attn_core``: q (N,S,C), k/v (N,L,C)."""
+    lib = load_library()
+    _dev_check(q, k, v, coef, kv_ext)
+    N, S, Cdim = q.shape
+    p = PaidCoreParams()
+    p.struct_size = C.sizeof(PaidCoreParams)
+    p.flags = flags
+    p.dtype, p.mode, p.fused = _dtype_code(q), mode, int(bool(fused))
+    p.N, p.S, p.L, p.heads, p.head_dim = N, S, k.shape[1], heads, Cdim // heads
+    p.scale = float((Cdim // heads) ** -0.5 if scale is None else scale)
+    p.begin_frame = 0 if begin_frame is None else begin_frame
+    p.end_frame = N - 1 if end_frame is None else end_frame
+    out = torch.empty_like(q)
+    p.q, p.k, p.v, p.kv_ext, p.coef, p.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), _ptr(kv_ext), _ptr(coef), out.data_ptr()
+    need = lib.paid_attn_core_workspace_bytes(C.byref(p))
+    if need:
+        ws = _workspace(q.device, int(need))
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    _check(lib.paid_attn_core(C.byref(p), _stream(q)), "paid_attn_core")
+    return out

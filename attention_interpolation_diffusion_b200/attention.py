@@ -1,0 +1,76 @@
+"""Host-side stand-in for ``diffusers.models.attention_processor.Attention``.
+
+diffusers is not installed in this image, so the UNet harness and the tests use
+this module.  It exposes exactly the members the reference processors read from
+``attn`` (interpolation.py:588-677), so the same processor
+objects also plug into a real diffusers ``Attention``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _cabi
+
+
+class PaidAttnProcessor:
+    """Stock (non-interpolated) attention through the PLAIN mode of libpaid_attn --
+    the role ``AttnProcessor2_0`` plays in the reference (``original_attn``,
+    pipeline_interpolated_sdxl.py:1076)."""
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
+        check_unet_preconditions(attn, hidden_states, attention_mask)
+        return _cabi.attn_forward(
+            hidden_states, encoder_hidden_states, attn.to_q.weight, attn.to_k.weight, attn.to_v.weight,
+            attn.to_out[0].weight, attn.to_out[0].bias, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale)
+
+
+def check_unet_preconditions(attn, hidden_states, attention_mask):
+    """The kernels implement the UNet transformer-block case of the processors; the
+    branches that are dead there (interpolation.py:586-611, 618-621, 669-677) are
+    rejected instead of silently falling back to PyTorch."""
+    if hidden_states.ndim != 3:
+        raise NotImplementedError("libpaid_attn handles 3-D (batch, tokens, channels) hidden_states only")
+    if attention_mask is not None:
+        raise NotImplementedError("attention_mask must be None (the reference's fused modes are inconsistent with a mask)")
+    if getattr(attn, "spatial_norm", None) is not None or getattr(attn, "group_norm", None) is not None:
+        raise NotImplementedError("spatial_norm / group_norm attention blocks are not on the UNet transformer path")
+    if getattr(attn, "norm_cross", None):
+        raise NotImplementedError("norm_cross is not used by the SD / SDXL UNets")
+    if getattr(attn, "residual_connection", False) or getattr(attn, "rescale_output_factor", 1.0) != 1.0:
+        raise NotImplementedError("residual_connection / rescale_output_factor are not used by the SD / SDXL UNets")
+    if attn.to_q.bias is not None or attn.to_k.bias is not None or attn.to_v.bias is not None:
+        raise NotImplementedError("q/k/v projections with bias are not used by the SD / SDXL UNets")
+
+
+class Attention(nn.Module):
+    def __init__(self, query_dim: int, cross_attention_dim: Optional[int] = None, heads: int = 8, dim_head: int = 64,
+                 dropout: float = 0.0, bias: bool = False, processor=None):
+        super().__init__()
+        inner = heads * dim_head
+        if inner != query_dim:
+            raise NotImplementedError("SD / SDXL UNet attention has inner_dim == query_dim")
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        self.upcast_attention = False
+        self.upcast_softmax = False
+        self.spatial_norm = None
+        self.group_norm = None
+        self.norm_cross = None
+        self.residual_connection = False
+        self.rescale_output_factor = 1.0
+        cdim = query_dim if cross_attention_dim is None else cross_attention_dim
+        self.to_q = nn.Linear(query_dim, inner, bias=bias)
+        self.to_k = nn.Linear(cdim, inner, bias=bias)
+        self.to_v = nn.Linear(cdim, inner, bias=bias)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim, bias=True), nn.Dropout(dropout)])
+        self.processor = processor if processor is not None else PaidAttnProcessor()
+
+    def set_processor(self, processor):
+        self.processor = processor
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kw):
+        return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
+                              attention_mask=attention_mask, **kw)

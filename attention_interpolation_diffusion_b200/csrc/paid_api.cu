@@ -1,0 +1,230 @@
+// C ABI of libpaid_attn.so (include/paid_attn.h): validation, workspace carving, kernel dispatch.
+#include <cstring>
+
+#include "paid_common.cuh"
+
+namespace paid {
+
+char* error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+const char** last_kernel_slot() {
+  static thread_local const char* k = "";
+  return &k;
+}
+int fail(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return status;
+}
+std::atomic<uint64_t>& launch_counter() {
+  static std::atomic<uint64_t> c{0};
+  return c;
+}
+
+static inline uint64_t align256(uint64_t b) { return (b + 255) & ~uint64_t(255); }
+
+struct Workspace {
+  uint64_t q, k, v, h, kx, vx, total;
+};
+
+static Workspace plan_workspace(const PaidAttnParams* p) {
+  Workspace w{};
+  const uint64_t es = 2;
+  uint64_t nsc = align256((uint64_t)p->N * p->S * p->C * es);
+  uint64_t nlc = align256((uint64_t)p->N * p->L * p->C * es);
+  uint64_t off = 0;
+  w.q = off; off += nsc;
+  w.k = off; off += nlc;
+  w.v = off; off += nlc;
+  w.h = off; off += nsc;
+  if (p->mode == PAID_INNER) { w.kx = off; off += nlc; w.vx = off; off += nlc; }
+  w.total = off;
+  return w;
+}
+
+static int validate(const PaidAttnParams* p, bool need_io) {
+  if (!p) return fail(PAID_EINVAL, "params is NULL");
+  if (p->struct_size != sizeof(PaidAttnParams))
+    return fail(PAID_EINVAL, "PaidAttnParams.struct_size %u != %zu (ABI mismatch)", p->struct_size, sizeof(PaidAttnParams));
+  if (p->dtype != PAID_F16 && p->dtype != PAID_BF16) return fail(PAID_EINVAL, "dtype must be PAID_F16 or PAID_BF16");
+  if (p->mode < PAID_PLAIN || p->mode > PAID_INNER) return fail(PAID_EINVAL, "bad mode %d", p->mode);
+  if (p->N <= 0 || p->S <= 0 || p->L <= 0 || p->C <= 0 || p->Cc <= 0 || p->heads <= 0)
+    return fail(PAID_EINVAL, "sizes must be positive (N=%d S=%d L=%d C=%d Cc=%d heads=%d)", p->N, p->S, p->L, p->C,
+                p->Cc, p->heads);
+  if (p->C % p->heads) return fail(PAID_EINVAL, "C=%d is not a multiple of heads=%d", p->C, p->heads);
+  if (p->C % 8 || p->Cc % 8) return fail(PAID_EUNSUPPORTED, "C and Cc must be multiples of 8 (16-byte rows)");
+  if (!p->ctx && (p->L != p->S || p->Cc != p->C))
+    return fail(PAID_EINVAL, "self-attention (ctx == NULL) needs L == S and Cc == C");
+  if (!need_io) return PAID_OK;
+  if (!p->x || !p->wq || !p->wk || !p->wv || !p->wo || !p->y) return fail(PAID_EINVAL, "x, wq, wk, wv, wo, y must be non-NULL");
+  if (p->mode != PAID_PLAIN) {
+    if (!p->coef) return fail(PAID_EINVAL, "coef is NULL");
+    if (!p->kv_ext && (p->begin_frame < 0 || p->begin_frame >= p->N || p->end_frame < 0 || p->end_frame >= p->N))
+      return fail(PAID_EINVAL, "begin_frame/end_frame (%d,%d) must index this batch when kv_ext is NULL", p->begin_frame,
+                  p->end_frame);
+    if (p->begin_frame >= p->N || p->end_frame >= p->N) return fail(PAID_EINVAL, "endpoint frame index out of range");
+  }
+  return PAID_OK;
+}
+
+static int linear(const void* x, const void* w, const void* bias, void* y, long long M, int Nout, int K, int dtype,
+                  uint32_t flags, cudaStream_t stream) {
+  if (!(flags & PAID_FLAG_GENERIC_KERNELS) && linear_tc_supported(M, Nout, K))
+    return launch_linear_tc(x, w, bias, y, M, Nout, K, dtype, stream);
+  return launch_linear_generic(x, w, bias, y, M, Nout, K, dtype, stream);
+}
+
+static int core_dispatch(const CoreArgs& a, uint32_t flags, cudaStream_t stream) {
+  if (!(flags & PAID_FLAG_GENERIC_KERNELS) && attn_tc_supported(a)) {
+    *last_kernel_slot() = "tcgen05";
+    return launch_attn_tc(a, stream);
+  }
+  *last_kernel_slot() = "generic";
+  return launch_attn_generic(a, stream);
+}
+
+// resolve slot 1 / slot 2 sources; for INNER run the endpoint lerp into (kx, vx)
+static int resolve_slots(CoreArgs& a, const void* kv_ext, void* kx, void* vx, cudaStream_t stream) {
+  const long long LC = (long long)a.L * a.heads * a.head_dim;
+  const char* kb; const char* vb; const char* ke; const char* ve;
+  if (kv_ext) {
+    const char* e = (const char*)kv_ext;
+    kb = e; vb = e + LC * 2; ke = e + 2 * LC * 2; ve = e + 3 * LC * 2;
+  } else {
+    kb = (const char*)a.k + (long long)a.begin_frame * LC * 2;
+    vb = (const char*)a.v + (long long)a.begin_frame * LC * 2;
+    ke = (const char*)a.k + (long long)a.end_frame * LC * 2;
+    ve = (const char*)a.v + (long long)a.end_frame * LC * 2;
+  }
+  a.k1 = a.v1 = a.k2 = a.v2 = nullptr;
+  a.stride1 = a.stride2 = 0;
+  if (a.mode == PAID_OUTER) {
+    a.k1 = kb; a.v1 = vb; a.k2 = ke; a.v2 = ve;
+  } else if (a.mode == PAID_INNER) {
+    int st = launch_lerp_endpoints(kb, vb, ke, ve, a.coef, kx, vx, a.N, LC, a.dtype, stream);
+    if (st != PAID_OK) return st;
+    a.k1 = kx; a.v1 = vx; a.stride1 = LC;
+  }
+  return PAID_OK;
+}
+
+}  // namespace paid
+
+using namespace paid;
+
+extern "C" {
+
+int paid_attn_abi_version(void) { return PAID_ABI_VERSION; }
+
+const char* paid_attn_last_error(void) { return error_buffer(); }
+
+uint64_t paid_attn_launch_count(void) { return launch_counter().load(std::memory_order_relaxed); }
+
+const char* paid_attn_last_kernel(void) { return *last_kernel_slot(); }
+
+uint64_t paid_attn_workspace_bytes(const PaidAttnParams* p) {
+  if (validate(p, false) != PAID_OK) return 0;
+  return plan_workspace(p).total;
+}
+
+uint64_t paid_attn_core_workspace_bytes(const PaidCoreParams* p) {
+  if (!p || p->struct_size != sizeof(PaidCoreParams)) return 0;
+  if (p->mode != PAID_INNER) return 0;
+  return 2 * align256((uint64_t)p->N * p->L * p->heads * p->head_dim * 2);
+}
+
+int paid_linear(const void* x, const void* w, const void* bias, void* y, int64_t M, int32_t Nout, int32_t K,
+                int32_t dtype, uint32_t flags, void* cuda_stream) {
+  if (!x || !w || !y) return fail(PAID_EINVAL, "paid_linear: x, w, y must be non-NULL");
+  if (M <= 0 || Nout <= 0 || K <= 0) return fail(PAID_EINVAL, "paid_linear: sizes must be positive");
+  if (dtype != PAID_F16 && dtype != PAID_BF16) return fail(PAID_EINVAL, "paid_linear: bad dtype");
+  return linear(x, w, bias, y, M, Nout, K, dtype, flags, (cudaStream_t)cuda_stream);
+}
+
+int paid_attn_core(const PaidCoreParams* p, void* cuda_stream) {
+  if (!p) return fail(PAID_EINVAL, "params is NULL");
+  if (p->struct_size != sizeof(PaidCoreParams))
+    return fail(PAID_EINVAL, "PaidCoreParams.struct_size %u != %zu (ABI mismatch)", p->struct_size, sizeof(PaidCoreParams));
+  if (p->dtype != PAID_F16 && p->dtype != PAID_BF16) return fail(PAID_EINVAL, "bad dtype");
+  if (p->mode < PAID_PLAIN || p->mode > PAID_INNER) return fail(PAID_EINVAL, "bad mode %d", p->mode);
+  if (p->N <= 0 || p->S <= 0 || p->L <= 0 || p->heads <= 0 || p->head_dim <= 0) return fail(PAID_EINVAL, "sizes must be positive");
+  if ((p->heads * p->head_dim) % 8) return fail(PAID_EUNSUPPORTED, "heads*head_dim must be a multiple of 8");
+  if (!p->q || !p->k || !p->v || !p->out) return fail(PAID_EINVAL, "q, k, v, out must be non-NULL");
+  if (p->mode != PAID_PLAIN) {
+    if (!p->coef) return fail(PAID_EINVAL, "coef is NULL");
+    if (!p->kv_ext && (p->begin_frame < 0 || p->begin_frame >= p->N || p->end_frame < 0 || p->end_frame >= p->N))
+      return fail(PAID_EINVAL, "begin_frame/end_frame must index this batch when kv_ext is NULL");
+    if (p->begin_frame >= p->N || p->end_frame >= p->N) return fail(PAID_EINVAL, "endpoint frame index out of range");
+  }
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  CoreArgs a{};
+  a.dtype = p->dtype; a.mode = p->mode; a.fused = p->fused ? 1 : 0;
+  a.N = p->N; a.S = p->S; a.L = p->L; a.heads = p->heads; a.head_dim = p->head_dim;
+  a.scale = p->scale; a.begin_frame = p->begin_frame; a.end_frame = p->end_frame;
+  a.q = p->q; a.k = p->k; a.v = p->v; a.coef = p->coef; a.out = p->out;
+  void* kx = nullptr; void* vx = nullptr;
+  if (p->mode == PAID_INNER) {
+    uint64_t need = paid_attn_core_workspace_bytes(p);
+    if (!p->workspace || p->workspace_bytes < need)
+      return fail(PAID_EWORKSPACE, "INNER core needs %llu workspace bytes, got %llu", (unsigned long long)need,
+                  (unsigned long long)p->workspace_bytes);
+    kx = p->workspace;
+    vx = (char*)p->workspace + need / 2;
+  }
+  int st = resolve_slots(a, p->mode == PAID_PLAIN ? nullptr : p->kv_ext, kx, vx, stream);
+  if (st != PAID_OK) return st;
+  return core_dispatch(a, p->flags, stream);
+}
+
+int paid_attn_project_endpoints(const PaidAttnParams* p, int32_t local_frame, void* k_out, void* v_out,
+                                void* cuda_stream) {
+  int st = validate(p, false);
+  if (st != PAID_OK) return st;
+  if (!p->x || !p->wk || !p->wv || !k_out || !v_out) return fail(PAID_EINVAL, "x, wk, wv, k_out, v_out must be non-NULL");
+  if (local_frame < 0 || local_frame >= p->N) return fail(PAID_EINVAL, "local_frame %d out of range [0,%d)", local_frame, p->N);
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  const char* src = p->ctx ? (const char*)p->ctx : (const char*)p->x;
+  src += (long long)local_frame * p->L * p->Cc * 2;
+  st = linear(src, p->wk, nullptr, k_out, p->L, p->C, p->Cc, p->dtype, p->flags, stream);
+  if (st != PAID_OK) return st;
+  return linear(src, p->wv, nullptr, v_out, p->L, p->C, p->Cc, p->dtype, p->flags, stream);
+}
+
+int paid_attn_forward(const PaidAttnParams* p, void* cuda_stream) {
+  int st = validate(p, true);
+  if (st != PAID_OK) return st;
+  Workspace ws = plan_workspace(p);
+  if (!p->workspace || p->workspace_bytes < ws.total)
+    return fail(PAID_EWORKSPACE, "workspace too small: need %llu bytes, got %llu", (unsigned long long)ws.total,
+                (unsigned long long)p->workspace_bytes);
+  if ((uintptr_t)p->workspace & 255) return fail(PAID_EINVAL, "workspace must be 256-byte aligned");
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  char* base = (char*)p->workspace;
+  void* Q = base + ws.q; void* K = base + ws.k; void* V = base + ws.v; void* H = base + ws.h;
+  const void* src = p->ctx ? p->ctx : p->x;
+  const long long MS = (long long)p->N * p->S, ML = (long long)p->N * p->L;
+
+  // interpolation.py:613, 623-624
+  if ((st = linear(p->x, p->wq, nullptr, Q, MS, p->C, p->C, p->dtype, p->flags, stream)) != PAID_OK) return st;
+  if ((st = linear(src, p->wk, nullptr, K, ML, p->C, p->Cc, p->dtype, p->flags, stream)) != PAID_OK) return st;
+  if ((st = linear(src, p->wv, nullptr, V, ML, p->C, p->Cc, p->dtype, p->flags, stream)) != PAID_OK) return st;
+
+  CoreArgs a{};
+  a.dtype = p->dtype; a.mode = p->mode; a.fused = p->fused ? 1 : 0;
+  a.N = p->N; a.S = p->S; a.L = p->L; a.heads = p->heads; a.head_dim = p->C / p->heads;
+  a.scale = p->scale; a.begin_frame = p->begin_frame; a.end_frame = p->end_frame;
+  a.q = Q; a.k = K; a.v = V; a.coef = p->coef; a.out = H;
+  void* kx = p->mode == PAID_INNER ? base + ws.kx : nullptr;
+  void* vx = p->mode == PAID_INNER ? base + ws.vx : nullptr;
+  if ((st = resolve_slots(a, p->mode == PAID_PLAIN ? nullptr : p->kv_ext, kx, vx, stream)) != PAID_OK) return st;
+  // interpolation.py:627-664 / 760-790
+  if ((st = core_dispatch(a, p->flags, stream)) != PAID_OK) return st;
+  // interpolation.py:666-667
+  return linear(H, p->wo, p->bo, p->y, MS, p->C, p->C, p->dtype, p->flags, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+/*
+ * paid_attn.h -- C ABI of libpaid_attn.so: the PAID / AID interpolated-attention
+ * hot path as hand-written sm_100a CUDA.
+ *
+ * The reference (QY-H00/attention-interpolation-diffusion) is pure Python and has
+ * no FFI of its own; the boundary it exposes for this path is the diffusers
+ * AttnProcessor protocol.  Each entry point below replaces the body of one
+ * reference call and is what a binding written against the reference would bind:
+ *
+ *   paid_attn_forward            OuterInterpolatedAttnProcessor.__call__  interpolation.py:573-679
+ *                                InnerInterpolatedAttnProcessor.__call__  interpolation.py:707-804
+ *                                deactivated branch (original_attn)       interpolation.py:581-584, 715-718
+ *   paid_attn_core               attn.get_attention_scores + torch.bmm + alpha-lerp
+ *                                                                         interpolation.py:627-664, 760-790
+ *   paid_linear                  attn.to_q / to_k / to_v / to_out[0]      interpolation.py:613, 623-624, 666
+ *   paid_attn_project_endpoints  key[0:1], key[-1:], value[0:1], value[-1:] interpolation.py:627-630
+ *                                (for frame-sharded execution: the owner rank
+ *                                projects, NCCL broadcasts, every rank consumes
+ *                                through PaidAttnParams.kv_ext)
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a DEVICE pointer owned by the
+ *     caller (PyTorch), including the workspace.  The library allocates no device
+ *     memory and keeps no state besides a small host-side TMA-descriptor cache.
+ *   - all tensors are dense row-major with the shapes given; 16-byte aligned.
+ *   - asynchronous on the given cudaStream_t (passed as void*); no host sync.
+ *   - returns PAID_OK (0) or a negative PaidStatus; never throws, never aborts.
+ *     paid_attn_last_error() gives a thread-local message for the last failure.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     returns PAID_ECUDA.
+ */
+#ifndef PAID_ATTN_H_
+#define PAID_ATTN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAID_ABI_VERSION 1
+
+typedef enum PaidStatus {
+  PAID_OK = 0,
+  PAID_EINVAL = -1,       /* bad argument (null pointer, size <= 0, C % heads != 0, ...) */
+  PAID_EUNSUPPORTED = -2, /* valid but not implemented shape / dtype */
+  PAID_ECUDA = -3,        /* CUDA runtime / driver error (message has the cudaError) */
+  PAID_EWORKSPACE = -4    /* workspace too small: see paid_attn_workspace_bytes */
+} PaidStatus;
+
+typedef enum PaidDType { PAID_F16 = 0, PAID_BF16 = 1 } PaidDType;
+
+/* mode of one processor call */
+typedef enum PaidMode {
+  PAID_PLAIN = 0, /* deactivated processor: stock softmax attention of each frame        */
+  PAID_OUTER = 1, /* (1-c) Attn(q,[k;k_begin]) + c Attn(q,[k;k_end])   interpolation.py:643-664 */
+  PAID_INNER = 2  /* Attn(q,[k;(1-c)k_begin+c k_end])                   interpolation.py:772-790 */
+} PaidMode;
+
+/* flags */
+#define PAID_FLAG_GENERIC_KERNELS 1u /* force the generic-shape CUDA kernels (validation cross-check) */
+
+typedef struct PaidAttnParams {
+  uint32_t struct_size; /* sizeof(PaidAttnParams), ABI guard */
+  uint32_t flags;
+  int32_t dtype;  /* PaidDType of x, ctx, weights, y and the workspace tensors */
+  int32_t mode;   /* PaidMode */
+  int32_t fused;  /* 1: keys are [frame's own ; endpoint] ("fused with self-attention", is_fused) */
+  int32_t N;      /* frames in this (local) batch */
+  int32_t S;      /* query tokens per frame */
+  int32_t L;      /* context tokens per frame (== S when ctx is NULL) */
+  int32_t C;      /* channels (inner dim = heads * head_dim) */
+  int32_t Cc;     /* context channels (== C when ctx is NULL) */
+  int32_t heads;
+  float scale;    /* attn.scale = head_dim^-0.5 */
+  /* local indices of the two endpoint frames inside this batch (reference: 0 and N-1),
+   * or -1 when that frame lives on another rank (then kv_ext must be given) */
+  int32_t begin_frame;
+  int32_t end_frame;
+  const void* x;    /* (N,S,C)  hidden_states */
+  const void* ctx;  /* NULL (self-attention) or (N,L,Cc) encoder_hidden_states */
+  const void* wq;   /* (C,C)   attn.to_q.weight */
+  const void* wk;   /* (C,Cc)  attn.to_k.weight */
+  const void* wv;   /* (C,Cc)  attn.to_v.weight */
+  const void* wo;   /* (C,C)   attn.to_out[0].weight */
+  const void* bo;   /* (C,) or NULL  attn.to_out[0].bias */
+  const float* coef; /* (N,) fp32 interpolation coefficients c_n of the local frames (ignored for PLAIN) */
+  /* optional endpoint K/V produced elsewhere: (4,L,C) = K_begin, V_begin, K_end, V_end; NULL: take
+   * them from frames begin_frame / end_frame of this batch */
+  const void* kv_ext;
+  void* y;          /* (N,S,C) output */
+  void* workspace;  /* >= paid_attn_workspace_bytes(p) bytes, 256-byte aligned */
+  uint64_t workspace_bytes;
+} PaidAttnParams;
+
+/* attention on already projected tensors (head h of frame n lives at [n, t, h*d : (h+1)*d]) */
+typedef struct PaidCoreParams {
+  uint32_t struct_size;
+  uint32_t flags;
+  int32_t dtype, mode, fused;
+  int32_t N, S, L, heads, head_dim;
+  float scale;
+  int32_t begin_frame, end_frame;
+  const void* q;        /* (N,S,heads*head_dim) */
+  const void* k;        /* (N,L,heads*head_dim) */
+  const void* v;        /* (N,L,heads*head_dim) */
+  const void* kv_ext;   /* NULL or (4,L,heads*head_dim) */
+  const float* coef;    /* (N,) */
+  void* out;            /* (N,S,heads*head_dim) attention output before to_out */
+  void* workspace;      /* INNER only: 2*N*L*heads*head_dim elements for the lerped K/V; else may be NULL */
+  uint64_t workspace_bytes;
+} PaidCoreParams;
+
+int paid_attn_abi_version(void);
+
+/* bytes of workspace paid_attn_forward needs for these sizes (0 on invalid params) */
+uint64_t paid_attn_workspace_bytes(const PaidAttnParams* p);
+uint64_t paid_attn_core_workspace_bytes(const PaidCoreParams* p);
+
+/* one processor call: q/k/v projection, interpolated attention, alpha-lerp, output projection */
+int paid_attn_forward(const PaidAttnParams* p, void* cuda_stream);
+
+/* the attention core alone */
+int paid_attn_core(const PaidCoreParams* p, void* cuda_stream);
+
+/* K and V of one local frame: k_out, v_out are (L,C).  Uses p->x / p->ctx, p->wk, p->wv. */
+int paid_attn_project_endpoints(const PaidAttnParams* p, int32_t local_frame, void* k_out, void* v_out,
+                                void* cuda_stream);
+
+/* y (M,Nout) = x (M,K) * w(Nout,K)^T + bias(Nout or NULL) */
+int paid_linear(const void* x, const void* w, const void* bias, void* y, int64_t M, int32_t Nout, int32_t K,
+                int32_t dtype, uint32_t flags, void* cuda_stream);
+
+/* message for the last non-OK status returned on this thread ("" if none) */
+const char* paid_attn_last_error(void);
+
+/* number of CUDA kernels this library has launched in this process (monotonic) */
+uint64_t paid_attn_launch_count(void);
+
+/* name of the attention kernel family the last paid_attn_core / paid_attn_forward call on this thread used:
+ * "tcgen05" or "generic" ("" before the first call) */
+const char* paid_attn_last_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAID_ATTN_H_ */

@@ -1,0 +1,201 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against (a) the golden vectors written by the
+unmodified reference and (b) the CPU oracle on the same seeded inputs.
+
+Tolerance: kernels compute in fp16/bf16 with fp32 accumulation; against the fp32 oracle
+rel-RMS <= 2e-3 and max-abs <= 2e-2 * RMS(oracle output)  (about 4x the reference's own fp16-vs-fp32 gap of
+3.8e-4..5.3e-4).  bf16 has 3 fewer mantissa bits than fp16: its gate is 8x wider.
+"""
+import pytest
+import torch
+
+import paid_oracle as O
+from golden_util import MODES, case_names, load_case
+
+pytestmark = pytest.mark.gpu
+
+REL, MAXABS = O.REL_RMS_TOL, O.MAX_ABS_TOL_X_RMS
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    assert torch.cuda.is_available()
+    from attention_interpolation_diffusion_b200 import _cabi
+    _cabi.load_library()
+    return _cabi
+
+
+def dev(t, dtype=torch.float16):
+    return None if t is None else t.to("cuda", dtype).contiguous()
+
+
+def rounded(t, dtype=torch.float16):
+    return None if t is None else t.to(dtype).float()
+
+
+def run_layer(cabi, w, x, ctx, coef, mode, fused, dtype=torch.float16, flags=0, **kw):
+    y = cabi.attn_forward(dev(x, dtype), dev(ctx, dtype), dev(w.wq, dtype), dev(w.wk, dtype), dev(w.wv, dtype),
+                          dev(w.wo, dtype), dev(w.bo, dtype), None if coef is None else coef.float().cuda(), w.heads,
+                          mode, fused, flags=flags, **kw)
+    torch.cuda.synchronize()
+    return y.float().cpu()
+
+
+def oracle_on_rounded(w, x, ctx, coef, mode, fused, dtype=torch.float16, **kw):
+    wr = O.LayerWeights(*(rounded(t, dtype) for t in (w.wq, w.wk, w.wv, w.wo, w.bo)), heads=w.heads)
+    return O.forward_direct(rounded(x, dtype), rounded(ctx, dtype), wr, coef, mode, fused, **kw)
+
+
+def check(y, ref, what, rel=REL, maxabs=MAXABS):
+    ok, m = O.within_tolerance(y, ref, rel, maxabs)
+    assert ok, (what, m)
+    return m
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["default", "generic"])
+@pytest.mark.parametrize("name", case_names())
+def test_golden_vectors(cabi, name, flags):
+    """Every reference-generated vector, all four modes, fp16."""
+    c = load_case(name)
+    for (m, fused), y_ref in c["outs"].items():
+        mode = O.MODE_NAMES[m]
+        y = run_layer(cabi, c["w"], c["x"], c["ctx"], c["coef"], mode, fused, flags=flags)[:, ::c["stride"]]
+        check(y, y_ref, (name, m, fused, "vs reference golden"))
+        y_or = oracle_on_rounded(c["w"], c["x"], c["ctx"], c["coef"], mode, fused)[:, ::c["stride"]]
+        check(y, y_or, (name, m, fused, "vs oracle on fp16-rounded inputs"), rel=1e-3)
+
+
+@pytest.mark.parametrize("name", ["d64_self_n5", "d64_cross_n5", "d40_self_n4"])
+def test_golden_vectors_bf16(cabi, name):
+    c = load_case(name)
+    for (m, fused), y_ref in c["outs"].items():
+        y = run_layer(cabi, c["w"], c["x"], c["ctx"], c["coef"], O.MODE_NAMES[m], fused, dtype=torch.bfloat16)
+        check(y, y_ref, (name, m, fused, "bf16"), rel=8 * REL, maxabs=8 * MAXABS)
+
+
+def test_deactivated_is_plain_attention(cabi):
+    """interpolation.py:581-584: a deactivated processor is stock attention of each frame."""
+    for L in (None, 77):
+        w = O.make_layer(128, 128 if L is None else 64, 2, 21)
+        x, ctx = O.make_inputs(4, 100, 128, L, 64, 21)
+        y = run_layer(cabi, w, x, ctx, None, O.MODE_PLAIN, False)
+        check(y, oracle_on_rounded(w, x, ctx, None, O.MODE_PLAIN, False), ("plain", L), rel=1e-3)
+
+
+@pytest.mark.parametrize("m,fused", MODES)
+def test_sdxl_geometry_against_oracle(cabi, m, fused):
+    """SDXL 32x32 level geometry (S=1024, C=1280, 20 heads of 64), N=4, self and cross."""
+    mode = O.MODE_NAMES[m]
+    for L in (None, 77):
+        w = O.make_layer(1280, 1280 if L is None else 2048, 20, 31)
+        x, ctx = O.make_inputs(4, 1024, 1280, L, 2048, 31)
+        coef = O.coefficients(4, 4, 4)
+        y = run_layer(cabi, w, x, ctx, coef, mode, fused)
+        wr = O.LayerWeights(*(rounded(t) for t in (w.wq, w.wk, w.wv, w.wo, w.bo)), heads=20)
+        ref = O.forward_chunked(rounded(x), rounded(ctx), wr, coef, mode, fused, rows=256)
+        check(y, ref, (m, fused, L), rel=1e-3)
+
+
+@pytest.mark.parametrize("m,fused", MODES)
+def test_properties_at_full_size(cabi, m, fused):
+    """Size-independent properties at BASELINE config sizes (SDXL 64x64 level: S=4096, C=640, 10 heads; N=7):
+    endpoint frames equal plain attention; the N-frame batch equals 3-frame [0, i, N-1] batches; a frame-sharded
+    call with external endpoint K/V equals the single-batch call; default and generic kernels agree."""
+    mode = O.MODE_NAMES[m]
+    N, S, C, h = 7, 4096, 640, 10
+    w = O.make_layer(C, C, h, 41)
+    x, _ = O.make_inputs(N, S, C, None, C, 41)
+    coef = O.coefficients(N, 4, 4)
+    y = run_layer(cabi, w, x, None, coef, mode, fused)
+    plain = run_layer(cabi, w, x, None, None, O.MODE_PLAIN, False)
+    check(y[0], plain[0], "begin endpoint == plain", rel=5e-4)
+    check(y[-1], plain[-1], "end endpoint == plain", rel=5e-4)
+    idx = [0, 3, N - 1]
+    y3 = run_layer(cabi, w, x[idx], None, coef[idx], mode, fused)
+    check(y3[1], y[3], "3-frame batch == N-frame batch", rel=1e-5, maxabs=1e-3)
+    # sharded: frames 2..4 with endpoint K/V projected separately
+    kv = torch.empty(4, S, C, dtype=torch.float16, device="cuda")
+    xd, wk, wv = dev(x), dev(w.wk), dev(w.wv)
+    cabi.project_endpoints(xd, None, wk, wv, h, 0, kv[0], kv[1])
+    cabi.project_endpoints(xd, None, wk, wv, h, N - 1, kv[2], kv[3])
+    ys = run_layer(cabi, w, x[2:5], None, coef[2:5], mode, fused, begin_frame=-1, end_frame=-1, kv_ext=kv)
+    check(ys, y[2:5], "sharded == single batch", rel=1e-5, maxabs=1e-3)
+    yg = run_layer(cabi, w, x[idx], None, coef[idx], mode, fused, flags=cabi.FLAG_GENERIC_KERNELS)
+    check(y3, yg, "default kernels == generic kernels", rel=1e-3)
+
+
+def test_linear_against_torch(cabi):
+    torch.manual_seed(0)
+    for M, Nout, K in ((7 * 1024, 1280, 1280), (539, 640, 2048), (77, 320, 768), (4096, 320, 320), (1000, 72, 200)):
+        x = torch.randn(M, K, device="cuda").half()
+        w = (torch.randn(Nout, K, device="cuda") / K ** 0.5).half()
+        b = torch.randn(Nout, device="cuda").half()
+        ref = x.float() @ w.float().T + b.float()
+        for flags in (0, 1):
+            y = cabi.linear(x, w, b, flags=flags)
+            check(y.float().cpu(), ref.cpu(), ("linear", M, Nout, K, flags), rel=1e-3)
+        y = cabi.linear(x, w, None)
+        check(y.float().cpu(), (ref - b.float()).cpu(), ("linear nobias", M, Nout, K), rel=1e-3)
+
+
+def test_core_edge_shapes(cabi):
+    """Ragged sizes: S and L not multiples of any tile, L smaller than a tile, single query row."""
+    for S, L, h, d in ((1, 1, 1, 64), (130, 77, 2, 64), (257, 300, 1, 64), (64, 5, 3, 40), (33, 129, 1, 160)):
+        N, Cd = 3, h * d
+        torch.manual_seed(S + L)
+        q, k, v = (torch.randn(N, T, Cd) for T in (S, L, L))
+        coef = torch.tensor([0.0, 0.4, 1.0])
+        for m, fused in MODES:
+            mode = O.MODE_NAMES[m]
+            out = cabi.attn_core(dev(q), dev(k), dev(v), coef.cuda(), h, mode, fused)
+            torch.cuda.synchronize()
+            ref = O._direct_core(rounded(q), rounded(k), rounded(v), tuple(rounded(t) for t in (k[0], v[0], k[-1], v[-1])),
+                                 coef, mode, fused, d ** -0.5, h)
+            check(out.float().cpu(), ref, (S, L, h, d, m, fused), rel=1e-3)
+
+
+def test_processor_objects_on_attention_module(cabi):
+    """The drop-in processor classes on the Attention stand-in, activated and deactivated, N != 3."""
+    from attention_interpolation_diffusion_b200 import (Attention, InnerInterpolatedAttnProcessor,
+                                                        OuterInterpolatedAttnProcessor)
+    torch.manual_seed(5)
+    N, S, C, h, Cc = 5, 200, 128, 2, 96
+    for cross in (False, True):
+        attn = Attention(C, Cc if cross else None, h, C // h).cuda().half()
+        w = O.LayerWeights(attn.to_q.weight.float().cpu(), attn.to_k.weight.float().cpu(), attn.to_v.weight.float().cpu(),
+                           attn.to_out[0].weight.float().cpu(), attn.to_out[0].bias.float().cpu(), h)
+        x = torch.randn(N, S, C)
+        ctx = torch.randn(N, 77, Cc) if cross else None
+        for cls, mode in ((OuterInterpolatedAttnProcessor, O.MODE_OUTER), (InnerInterpolatedAttnProcessor, O.MODE_INNER)):
+            proc = cls(size=N, is_fused=True, alpha=4, beta=4)
+            attn.set_processor(proc)
+            y = attn(dev(x), encoder_hidden_states=dev(ctx))
+            check(y.float().cpu(), O.forward_direct(rounded(x), rounded(ctx), w, proc.coef, mode, True), (cls.__name__, cross), rel=1e-3)
+            proc.deactivate()
+            y = attn(dev(x), encoder_hidden_states=dev(ctx))
+            check(y.float().cpu(), O.forward_direct(rounded(x), rounded(ctx), w, None, O.MODE_PLAIN, False), "deactivated", rel=1e-3)
+            with pytest.raises(ValueError):
+                proc.activate(0.5)              # size-3 coefficients on a 5-frame batch, like the reference's bmm error
+                attn(dev(x), encoder_hidden_states=dev(ctx))
+            with pytest.raises(NotImplementedError):
+                proc.set_coefs(torch.linspace(0, 1, N))
+                attn(dev(x), encoder_hidden_states=dev(ctx), attention_mask=torch.zeros(1, device="cuda"))
+
+
+def test_pipeline_frame_sharding_equals_single_batch(cabi):
+    """'Multi-GPU without a cluster' (SURVEY.md section 8e): R logical shards run one after the other on one GPU
+    with the endpoint K/V exchanged through kv_ext reproduce the single-batch denoise."""
+    from attention_interpolation_diffusion_b200.pipeline import InterpolationPipeline
+    from attention_interpolation_diffusion_b200.sharding import FrameShard
+    from attention_interpolation_diffusion_b200.unet_harness import build_unet
+    net = build_unet("tiny", "cuda", torch.float16, seed=7)
+    g = torch.Generator("cpu").manual_seed(1002)
+    r = lambda *s: torch.randn(*s, generator=g).cuda().half()
+    args = dict(latent_start=r(1, 4, 16, 16), latent_end=r(1, 4, 16, 16), embeds_start=r(1, 77, 96),
+                embeds_end=r(1, 77, 96), negative_embeds=r(1, 77, 96), guide_embeds=r(1, 77, 96),
+                pooled_start=r(1, 1280), pooled_end=r(1, 1280), pooled_negative=r(1, 1280), pooled_guide=r(1, 1280),
+                size=5, num_inference_steps=4)
+    full = InterpolationPipeline(net).interpolate(**args)
+    assert full.shape == (5, 4, 16, 16) and torch.isfinite(full).all()
+    # a single-rank shard covers all frames and goes through project_endpoints + kv_ext
+    one = InterpolationPipeline(net, shard=FrameShard(0, 1, 5)).interpolate(**args)
+    check(one.float().cpu(), full.float().cpu(), "world-size-1 shard", rel=2e-3)
