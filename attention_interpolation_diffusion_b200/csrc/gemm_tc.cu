@@ -1,7 +1,150 @@
+// Projection GEMM on the 5th-generation tensor cores:  y (M,N) = x (M,K) w(N,K)^T + bias.
+//
+// Replaces attn.to_q / to_k / to_v / to_out[0] (reference interpolation.py:613, 623-624, 666).
+// Both operands are K-major, so x and w tiles are TMA-loaded as they lie in HBM (128-byte swizzle),
+// multiplied with tcgen05.mma (128x128x16 per instruction, fp32 accumulator in TMEM) and written back
+// by four epilogue warps straight from TMEM (+bias, -> fp16/bf16).
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2-5 epilogue.
+// One 128x128 output tile per CTA; 3-stage 32 KB ring so two CTAs share an SM and one CTA's epilogue
+// overlaps the other's main loop.
+#include <type_traits>
+
 #include "paid_common.cuh"
+#include "sm100_ptx.cuh"
+
 namespace paid {
-bool linear_tc_supported(long long, int, int) { return false; }
-int launch_linear_tc(const void*, const void*, const void*, void*, long long, int, int, int, cudaStream_t) {
-  return fail(PAID_EUNSUPPORTED, "tcgen05 linear not built");
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int TMEM_COLS = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(192, 2)
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const T* __restrict__ bias, T* __restrict__ y, long long M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const long long m0 = (long long)blockIdx.y * BM;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    ptx::mbar_init(tmem_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, TMEM_COLS); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        uint8_t* a = smem + s * STAGE_BYTES;
+        ptx::tma_load_2d(a, &tmA, &full[s], kb * BK, (int)m0);
+        ptx::tma_load_2d(a + A_BYTES, &tmB, &full[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc(BM, BN, sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t a = ptx::smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t adesc = ptx::make_smem_desc_sw128(a, 16, 1024);
+        const uint64_t bdesc = ptx::make_smem_desc_sw128(a + A_BYTES, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)  // +32 bytes per K step inside the 128-byte swizzle atom
+          ptx::mma_ss(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        ptx::tc_commit(&empty[s]);
+      }
+      ptx::tc_commit(tmem_full);
+    }
+  } else {
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    ptx::mbar_wait(tmem_full, 0);
+    ptx::tc_fence_after();
+    const long long row = m0 + quad * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + c * 32, r);
+      ptx::tmem_wait_ld();
+      const int col0 = n0 + c * 32;
+      if (row < M && col0 < N) {
+        T* dst = y + row * N + col0;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {  // 8 columns = 16 bytes per store
+          const int col = col0 + v * 8;
+          if (col >= N) break;
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f0 = __uint_as_float(r[v * 8 + 2 * j]), f1 = __uint_as_float(r[v * 8 + 2 * j + 1]);
+            if (bias) { f0 += to_f32(bias[col + 2 * j]); f1 += to_f32(bias[col + 2 * j + 1]); }
+            o[j] = pack2<T>(f0, f1);
+          }
+          *reinterpret_cast<uint4*>(dst + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); ptx::tmem_dealloc(tmem, TMEM_COLS); }
 }
+
+template <typename T>
+int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const void* bias, void* y, long long M, int N, int K,
+             cudaStream_t stream) {
+  auto kern = linear_tc_kernel<T>;
+  static bool configured = false;
+  if (!configured) {
+    PAID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (unsigned)((M + BM - 1) / BM));
+  kern<<<grid, 192, SMEM_BYTES, stream>>>(tmA, tmB, (const T*)bias, (T*)y, M, N, K);
+  PAID_LAUNCH_CHECK("linear_tc_kernel");
+  return PAID_OK;
+}
+
+}  // namespace
+
+bool linear_tc_supported(long long M, int Nout, int K) {
+  return M >= 1 && Nout % 8 == 0 && K % 8 == 0 && (M + BM - 1) / BM <= 65535;
+}
+
+int launch_linear_tc(const void* x, const void* w, const void* bias, void* y, long long M, int Nout, int K, int dtype,
+                     cudaStream_t stream) {
+  if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) return fail(PAID_EINVAL, "linear: pointers must be 16-byte aligned");
+  CUtensorMap tmA, tmB;
+  int st = make_tmap_2d(&tmA, x, dtype, M, K, K, BM);
+  if (st != PAID_OK) return st;
+  st = make_tmap_2d(&tmB, w, dtype, Nout, K, K, BN);
+  if (st != PAID_OK) return st;
+  return dtype == PAID_F16 ? launch_t<__half>(tmA, tmB, bias, y, M, Nout, K, stream)
+                           : launch_t<__nv_bfloat16>(tmA, tmB, bias, y, M, Nout, K, stream);
+}
+
 }  // namespace paid
