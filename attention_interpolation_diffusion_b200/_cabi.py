@@ -25,7 +25,7 @@ MODES = {"plain": PAID_PLAIN, "outer": PAID_OUTER, "inner": PAID_INNER}
 EXPORTS = [
     "paid_attn_abi_version", "paid_attn_workspace_bytes", "paid_attn_core_workspace_bytes", "paid_attn_forward",
     "paid_attn_core", "paid_attn_project_endpoints", "paid_linear", "paid_attn_last_error",
-    "paid_attn_launch_count", "paid_attn_last_kernel",
+    "paid_attn_launch_count", "paid_attn_last_kernel", "paid_attn_profile_enable", "paid_attn_profile_read",
 ]
 
 
@@ -83,6 +83,10 @@ def load_library() -> C.CDLL:
     lib.paid_attn_last_error.restype = C.c_char_p
     lib.paid_attn_launch_count.restype = C.c_uint64
     lib.paid_attn_last_kernel.restype = C.c_char_p
+    lib.paid_attn_profile_enable.restype = C.c_int
+    lib.paid_attn_profile_enable.argtypes = [C.c_int]
+    lib.paid_attn_profile_read.restype = C.c_int
+    lib.paid_attn_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.c_int]
     if lib.paid_attn_abi_version() != 1:
         raise RuntimeError("libpaid_attn.so ABI version mismatch")
     _lib = lib
@@ -99,6 +103,18 @@ def last_kernel() -> str:
 
 def launch_count() -> int:
     return int(load_library().paid_attn_launch_count())
+
+
+def profile_enable(on: bool):
+    _check(load_library().paid_attn_profile_enable(int(on)), "paid_attn_profile_enable")
+
+
+def profile_read(reset: bool = True):
+    """(total kernel ms, launches, algorithmic flops) of the attention-core launches since the last reset."""
+    ms, n, fl = C.c_double(0), C.c_uint64(0), C.c_double(0)
+    _check(load_library().paid_attn_profile_read(C.byref(ms), C.byref(n), C.byref(fl), int(reset)),
+           "paid_attn_profile_read")
+    return ms.value, int(n.value), fl.value
 
 
 def _check(status: int, what: str):

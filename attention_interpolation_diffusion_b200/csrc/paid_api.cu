@@ -1,5 +1,8 @@
 // C ABI of libpaid_attn.so (include/paid_attn.h): validation, workspace carving, kernel dispatch.
 #include <cstring>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "paid_common.cuh"
 
@@ -78,13 +81,48 @@ static int linear(const void* x, const void* w, const void* bias, void* y, long 
   return launch_linear_generic(x, w, bias, y, M, Nout, K, dtype, stream);
 }
 
+// ---- measurement hook: CUDA events around the attention-core kernel ------------------------------
+struct ProfileState {
+  std::mutex mu;
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> used, pool;
+  double alg_flops = 0;
+};
+static ProfileState& prof() {
+  static ProfileState p;
+  return p;
+}
+static double algorithmic_flops(const CoreArgs& a) {
+  const double A = 2.0 * a.N * a.S * a.L * a.heads * a.head_dim;
+  if (a.mode == PAID_OUTER) return (a.fused ? 6.0 : 4.0) * A;
+  if (a.mode == PAID_INNER) return (a.fused ? 4.0 : 2.0) * A;
+  return 2.0 * A;
+}
+
 static int core_dispatch(const CoreArgs& a, uint32_t flags, cudaStream_t stream) {
+  ProfileState& ps = prof();
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  if (ps.on) {
+    std::lock_guard<std::mutex> lk(ps.mu);
+    if (!ps.pool.empty()) { ev = ps.pool.back(); ps.pool.pop_back(); }
+    else { PAID_CUDA_CHECK(cudaEventCreate(&ev.first)); PAID_CUDA_CHECK(cudaEventCreate(&ev.second)); }
+    PAID_CUDA_CHECK(cudaEventRecord(ev.first, stream));
+  }
+  int st;
   if (!(flags & PAID_FLAG_GENERIC_KERNELS) && attn_tc_supported(a)) {
     *last_kernel_slot() = "tcgen05";
-    return launch_attn_tc(a, stream);
+    st = launch_attn_tc(a, stream);
+  } else {
+    *last_kernel_slot() = "generic";
+    st = launch_attn_generic(a, stream);
   }
-  *last_kernel_slot() = "generic";
-  return launch_attn_generic(a, stream);
+  if (ev.first) {
+    PAID_CUDA_CHECK(cudaEventRecord(ev.second, stream));
+    std::lock_guard<std::mutex> lk(ps.mu);
+    ps.used.push_back(ev);
+    ps.alg_flops += algorithmic_flops(a);
+  }
+  return st;
 }
 
 // resolve slot 1 / slot 2 sources; for INNER run the endpoint lerp into (kx, vx)
@@ -125,6 +163,34 @@ const char* paid_attn_last_error(void) { return error_buffer(); }
 uint64_t paid_attn_launch_count(void) { return launch_counter().load(std::memory_order_relaxed); }
 
 const char* paid_attn_last_kernel(void) { return *last_kernel_slot(); }
+
+int paid_attn_profile_enable(int on) {
+  ProfileState& ps = prof();
+  std::lock_guard<std::mutex> lk(ps.mu);
+  ps.on = on != 0;
+  return PAID_OK;
+}
+
+int paid_attn_profile_read(double* total_ms, uint64_t* launches, double* alg_flops, int reset) {
+  ProfileState& ps = prof();
+  std::lock_guard<std::mutex> lk(ps.mu);
+  double ms = 0;
+  for (auto& ev : ps.used) {
+    PAID_CUDA_CHECK(cudaEventSynchronize(ev.second));
+    float t = 0;
+    PAID_CUDA_CHECK(cudaEventElapsedTime(&t, ev.first, ev.second));
+    ms += t;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = ps.used.size();
+  if (alg_flops) *alg_flops = ps.alg_flops;
+  if (reset) {
+    for (auto& ev : ps.used) ps.pool.push_back(ev);
+    ps.used.clear();
+    ps.alg_flops = 0;
+  }
+  return PAID_OK;
+}
 
 uint64_t paid_attn_workspace_bytes(const PaidAttnParams* p) {
   if (validate(p, false) != PAID_OK) return 0;

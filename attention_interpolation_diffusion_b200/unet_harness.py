@@ -282,4 +282,7 @@ def build_unet(name: str, device="cuda", dtype=torch.float16, seed: int = 1002) 
     torch.manual_seed(seed)
     with torch.device(device):
         net = UNetHarness(CONFIGS[name])
-    return net.to(dtype=dtype).eval().requires_grad_(False)
+    net = net.to(dtype=dtype).eval().requires_grad_(False)
+    if torch.device(device).type == "cuda":
+        net = net.to(memory_format=torch.channels_last)   # NHWC convs; the token view of a feature map is then free
+    return net

@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- interpolation-frames/sec of an N-frame SDXL PAID sequence (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (own arm: the sm_100a CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  (reference arm: CPU port of the reference path)
+
+One "step" = one whole 50-step denoise of the frame sequence through the reference-shaped pipeline
+(`InterpolationPipeline.interpolate`): per denoising step one conditional UNet pass with fused-outer AID in every
+one of the 140 attention layers (first int(50*0.5)=25 steps) and one unconditional pass with plain attention.
+Workload at N=1: BASELINE.json configs[2] "SDXL 128x128 latent, 7-frame PAID (guidance prompt), 50 steps";
+at R GPUs the sequence has 7*R frames, frame-sharded (weak scaling) with one NCCL broadcast of the endpoint K/V per
+interpolated attention call.  Synthetic latents / embeddings (seed 1002) and random-init UNet weights.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES_PER_GPU = 7
+STEPS_PER_SEQUENCE = 50
+WARMUP_RATIO = 0.5
+METRIC = "interpolation-frames/sec (SDXL UNet, 50 steps)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--model", default="sdxl", choices=["sdxl", "sd15", "tiny"])
+    ap.add_argument("--frames", type=int, default=0, help="total frames of the sequence (default 7 per GPU)")
+    ap.add_argument("--atype", default="fused_outer", choices=["fused_outer", "fused_inner"])
+    ap.add_argument("--denoise-steps", type=int, default=STEPS_PER_SEQUENCE)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks: sampled with nvidia-smi DURING the timed region (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic inputs: seed 1002, N(0,1) latents and embeddings
+# ---------------------------------------------------------------------------------------------------------
+def make_host_inputs(cfg, dtype):
+    import torch
+    g = torch.Generator("cpu").manual_seed(1002)
+    r = lambda *s: torch.randn(*s, generator=g).to(dtype).pin_memory() if torch.cuda.is_available() else torch.randn(*s, generator=g).to(dtype)
+    side, cc = cfg.sample_size, cfg.cross_attention_dim
+    d = dict(latent_start=r(1, 4, side, side), latent_end=r(1, 4, side, side), embeds_start=r(1, 77, cc),
+             embeds_end=r(1, 77, cc), negative_embeds=r(1, 77, cc), guide_embeds=r(1, 77, cc))
+    if cfg.text_time:
+        d.update(pooled_start=r(1, 1280), pooled_end=r(1, 1280), pooled_negative=r(1, 1280), pooled_guide=r(1, 1280))
+    return d
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return j["bf16_tflops_sustained"], j["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained bf16 GEMM)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference processors, timed on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_frames_per_sec(model: str, frames: int, atype: str, denoise_steps: int, budget_rows: int = 256):
+    """Times the reference's attention path (oracle port of interpolation.py:573-804 hosted on the Attention
+    stand-in; diffusers itself is not installed) on a BOUNDED sample and extrapolates to one whole sequence:
+    per distinct attention-layer geometry of the UNet, one interpolated call and one plain call on `budget_rows`
+    query rows of every frame (full keys), scaled by S / rows and by the number of such layers and forwards.
+    Non-attention UNet blocks are NOT included (they are outside the hot path), which favours the CPU number."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import paid_oracle as O
+    from attention_interpolation_diffusion_b200.unet_harness import CONFIGS, UNetHarness
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    with torch.device("meta"):
+        geo = UNetHarness(CONFIGS[model]).attention_geometry()
+    classes = {}
+    for g in geo:
+        key = (g["S"], g["L"], g["C"], g["Cc"], g["heads"], g["self_attn"])
+        classes[key] = classes.get(key, 0) + 1
+    mode = O.MODE_OUTER if atype == "fused_outer" else O.MODE_INNER
+    coef = O.coefficients(frames, 4, 4)
+    t_aid = t_plain = 0.0
+    for (S, L, C, Cc, h, is_self), count in classes.items():
+        w = O.make_layer(C, Cc, h, seed=1)
+        x, ctx = O.make_inputs(frames, S, C, None if is_self else L, Cc, seed=1)
+        rows = min(S, budget_rows)
+        for m, fused in ((mode, True), (O.MODE_PLAIN, False)):
+            t0 = time.perf_counter()
+            q, k, v = O._project(x, ctx, w)                       # q/k/v projections, full size
+            t1 = time.perf_counter()
+            ends = (k[0], v[0], k[-1], v[-1])
+            hid = torch.zeros_like(q)
+            for n in range(frames):                               # attention core on the row sample
+                hid[n:n + 1, :rows] = O._direct_core(q[n:n + 1, :rows], k[n:n + 1], v[n:n + 1], ends, coef[n:n + 1],
+                                                     m, fused, (C // h) ** -0.5, h)
+            t2 = time.perf_counter()
+            _ = hid @ w.wo.T + w.bo                               # output projection, full size
+            t3 = time.perf_counter()
+            t_full = (t1 - t0) + (t3 - t2) + (t2 - t1) * (S / rows)
+            if m == O.MODE_PLAIN:
+                t_plain += count * t_full
+            else:
+                t_aid += count * t_full
+    n_aid = int(denoise_steps * WARMUP_RATIO)
+    n_plain = 2 * denoise_steps - n_aid
+    seq_s = n_aid * t_aid + n_plain * t_plain
+    sample = (f"oracle port, attention stack only: per layer geometry {budget_rows} query rows of each of {frames} frames "
+              f"(full keys), 1 AID + 1 plain call, extrapolated x S/rows x layer count x ({n_aid} AID + {n_plain} plain forwards)")
+    return frames / seq_s, cores, sample, {"t_aid_forward_s": t_aid, "t_plain_forward_s": t_plain}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = args.frames or FRAMES_PER_GPU * args.gpus
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, cores, sample, _ = cpu_reference_frames_per_sec(args.model, frames, args.atype, args.denoise_steps,
+                                                           budget_rows=128)
+        if i >= args.warmup:
+            vals.append(v)
+    value = statistics.mean(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * frames / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, frames),
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, frames):
+    name = {"sdxl": "SDXL 128x128 latent", "sd15": "SD1.5 64x64 latent", "tiny": "tiny test UNet"}[args.model]
+    return {"workload": f"{name}, {frames}-frame PAID (guide prompt), {args.atype} AID in all attention layers, "
+                        f"{args.denoise_steps} steps, warmup_ratio {WARMUP_RATIO}, CFG (2 UNet passes/step)",
+            "frames": frames, "frames_per_gpu": frames // max(args.gpus, 1), "denoise_steps": args.denoise_steps,
+            "parallelism": f"frame-sharded x{args.gpus}" if args.gpus > 1 else "single GPU",
+            "l2": "working set (5.1 GB fp16 UNet weights + activations) is far larger than the 126 MB L2; no explicit flush"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_own_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from attention_interpolation_diffusion_b200 import _cabi
+    from attention_interpolation_diffusion_b200.pipeline import InterpolationPipeline
+    from attention_interpolation_diffusion_b200.sharding import FrameShard
+    from attention_interpolation_diffusion_b200.unet_harness import build_unet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (own arm) needs a CUDA device: there is no CPU path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.load_library()
+    torch.backends.cudnn.benchmark = True
+    frames = args.frames or FRAMES_PER_GPU * world
+    dtype = torch.float16
+    net = build_unet(args.model, dev, dtype, seed=1002)
+    shard = FrameShard(rank, world, frames, None) if world > 1 else None
+    pipe = InterpolationPipeline(net, shard=shard)
+    pipe.load_aid(t=None, is_fused=True, atype=args.atype, size=frames, alpha=4, beta=4)
+    host = make_host_inputs(net.cfg, dtype)
+    devin = {k: v.to(dev) for k, v in host.items()}
+    kw = dict(size=frames, alpha=4.0, beta=4.0, num_inference_steps=args.denoise_steps, warmup_ratio=WARMUP_RATIO)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    step_dev = lambda: pipe.interpolate(**devin, **kw)
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        return pipe.interpolate(**d, **kw).float().cpu()
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local)
+    sampler.start()
+    _cabi.profile_read(reset=True)
+    _cabi.profile_enable(True)
+    launches0 = _cabi.launch_count()
+    ms = timed(step_dev, args.steps)
+    launches = _cabi.launch_count() - launches0
+    _cabi.profile_enable(False)
+    k_ms, k_launches, k_flops = _cabi.profile_read(reset=True)
+    clocks = sampler.stop()
+    value = frames * args.steps / (ms / 1000.0)
+
+    e2e = None
+    if not args.no_e2e:
+        out = step_e2e()
+        ms_e = timed(step_e2e, args.steps)
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        e2e = {"value": frames * args.steps / (ms_e / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": out.numel() * 4, "finite": bool(out.isfinite().all())}
+
+    if rank == 0:
+        peak_tf, _, peak_src = peaks()
+        achieved = k_flops / (k_ms / 1000.0) / 1e12 if k_ms > 0 else None
+        roofline = {"kernel": f"attention core ({_cabi.last_kernel()})", "bound": "tensor", "achieved": achieved,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None,
+                    "peak_source": peak_src, "traffic": None, "launches": k_launches,
+                    "avg_launch_ms": k_ms / max(k_launches, 1), "share_of_step": k_ms / ms,
+                    "how": "CUDA events around every attention-core launch of the timed region (rank 0); algorithmic "
+                           "flops per SURVEY.md 8d (fused-outer 6A, fused-inner 4A, plain 2A; A = 2 N S L C)"}
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(args, frames),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample, extra = cpu_reference_frames_per_sec(args.model, frames, args.atype, args.denoise_steps)
+            line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample, **extra}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_own_arm(a)

@@ -141,6 +141,14 @@ uint64_t paid_attn_launch_count(void);
  * "tcgen05" or "generic" ("" before the first call) */
 const char* paid_attn_last_kernel(void);
 
+/* Measurement hook (bench.py roofline): while enabled, every attention-core kernel launched by
+ * paid_attn_forward / paid_attn_core is bracketed by CUDA events on the launching stream.
+ * paid_attn_profile_read synchronises those events and returns, for the launches since the last reset, the
+ * summed kernel time, the launch count and the summed ALGORITHMIC flops (SURVEY.md section 8d:
+ * A = 2 N S L C per partial attention; outer-fused 6A, outer-pure 4A, inner-fused 4A, inner-pure / plain 2A). */
+int paid_attn_profile_enable(int on);
+int paid_attn_profile_read(double* total_ms, uint64_t* launches, double* alg_flops, int reset);
+
 #ifdef __cplusplus
 }
 #endif
