@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpaid_attn.so")
+LIB_PATH = os.environ.get("PAID_LIB_PATH") or os.path.join(_HERE, "lib", "libpaid_attn.so")
 
 PAID_OK, PAID_EINVAL, PAID_EUNSUPPORTED, PAID_ECUDA, PAID_EWORKSPACE = 0, -1, -2, -3, -4
 PAID_F16, PAID_BF16 = 0, 1

@@ -4,23 +4,28 @@
 // concatenations, the two materialised softmax(QK^T) matrices, the two P.V products and the alpha-lerp
 // (interpolation.py:627-664 outer, 760-790 inner; deactivated 581-584) with ONE kernel launch.
 //
-// Work decomposition: one CTA per (frame n, head, 256 query rows) = two 128-row Q tiles.  The keys of a
-// frame are up to three "slots" (own K/V, endpoint A, endpoint B; paid_common.cuh) streamed in steps of 64
-// keys.  Every slot has its own fp32 output accumulator in TMEM and its own online-softmax statistics; the
-// slots are merged (log-sum-exp) and alpha-lerped in the epilogue, so the endpoint K/V are read once and
-// never replicated or concatenated.
+// Formulation.  The output of frame n is  wA * softmax-attn(q, keys_A) + wB * softmax-attn(q, keys_B)  with
+//   stream A keys = [own K/V (if fused) ; endpoint slot 1],   stream B keys = [own K/V (if fused) ; slot 2]
+// (paid_common.cuh FramePlan).  Each stream is one flash-style online softmax with its own fp32 accumulator
+// in TMEM.  The shared "own K/V" segment is scored and exponentiated ONCE (both streams have identical
+// running statistics while they have seen the same keys) and its P.V product is issued into both
+// accumulators; endpoint K/V are read once per CTA and never replicated or concatenated.
 //
-//   warp 0        TMA producer: Q tiles once, then K / V tiles into an 8-stage shared-memory ring
-//   warp 1        tcgen05.mma issuer: S_t = Q_t K^T (SS), O_{t,slot} += P_t V (A operand from TMEM)
+// Work decomposition: one CTA per (frame, head, 256 query rows) = two 128-row Q tiles sharing every K/V tile.
+//   warp 0        TMA producer: Q tiles once, then K / V tiles (128 keys) into a 4-stage shared-memory ring
+//   warp 1        tcgen05.mma issuer: S_t = Q_t K^T (SS), acc_{t,stream} += P_t V (A operand P from TMEM)
 //   warps 2-5     softmax warpgroup of Q tile 0 (one thread per query row)
 //   warps 6-9     softmax warpgroup of Q tile 1
-//
-// TMEM (512 columns): S_0 [0,64) S_1 [64,128) (P_t aliases the low 32 columns of S_t as packed 16-bit),
-// O_{t,slot} at 128 + (3 t + slot) * 64.
+// TMEM (512 columns): S_t at 128 t (P_t aliases its low 64 columns as packed 16-bit), acc_{t,stream} at
+// 256 + 128 t + 64 stream.
 #include <type_traits>
 
 #include "paid_common.cuh"
 #include "sm100_ptx.cuh"
+
+#ifndef PAID_ABLATE
+#define PAID_ABLATE 0  // experiments only: 1 no MUFU, 2 no P store, 4 no max, 8 no P.V MMA, 16 no S load
+#endif
 
 namespace paid {
 namespace {
@@ -28,14 +33,15 @@ namespace {
 constexpr int D = 64;            // head_dim
 constexpr int BM = 128;          // rows per Q tile
 constexpr int QT = 2;            // Q tiles per CTA
-constexpr int BN = 64;           // keys per step
-constexpr int ST = 8;            // K/V ring stages
+constexpr int BN = 128;          // keys per step
+constexpr int ST = 4;            // K/V ring stages
 constexpr int Q_BYTES = BM * D * 2;    // 16 KB
-constexpr int KV_BYTES = BN * D * 2;   // 8 KB
+constexpr int KV_BYTES = BN * D * 2;   // 16 KB
 constexpr int SMEM_BYTES = 1024 + QT * Q_BYTES + ST * 2 * KV_BYTES + 512;
-constexpr int NUM_THREADS = 32 * (2 + 4 * QT);
-constexpr uint32_t TMEM_S = 0, TMEM_O = 128;
-constexpr float kRescaleThreshold = 8.f;  // log2 units: rescale O only when the running max grew by > 2^8
+constexpr int NUM_THREADS = 128 * (1 + QT);  // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1..QT: softmax
+constexpr int kRegsControl = 56, kRegsSoftmax = 224;  // setmaxnreg split of the 64K register file
+constexpr uint32_t TMEM_S = 0, TMEM_ACC = 256;
+constexpr float kRescaleThreshold = 8.f;  // log2 units: rescale an accumulator only when its max grew by > 2^8
 
 struct TcArgs {
   int mode, fused, N, S, L, heads, begin_frame, end_frame;
@@ -52,6 +58,25 @@ struct Barriers {
   uint32_t tmem_slot;
 };
 
+// key segments of one frame: K/V slot and the streams it feeds (bit 0: A, bit 1: B)
+struct Segments {
+  int count;
+  int slot[3];
+  int feeds[3];
+  bool a_active, b_active;
+};
+
+__device__ __forceinline__ Segments make_segments(const FramePlan& p) {
+  Segments g;
+  g.count = 0;
+  g.a_active = p.wA != 0.f;
+  g.b_active = p.wB != 0.f;
+  if (p.use0) { g.slot[g.count] = 0; g.feeds[g.count] = (g.a_active ? 1 : 0) | (g.b_active ? 2 : 0); ++g.count; }
+  if (p.use1) { g.slot[g.count] = 1; g.feeds[g.count] = 1; ++g.count; }
+  if (p.use2) { g.slot[g.count] = 2; g.feeds[g.count] = 2; ++g.count; }
+  return g;
+}
+
 __device__ __forceinline__ int frame_of_block(int z, int N) {
   // heavy (interior) frames first, the two cheap endpoint frames last
   if (N < 3) return z;
@@ -67,17 +92,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                              // [QT][128][64]
-  uint8_t* sK = sQ + QT * Q_BYTES;                 // [ST][64][64]
-  uint8_t* sV = sK + ST * KV_BYTES;                // [ST][64][64]
+  uint8_t* sK = sQ + QT * Q_BYTES;                 // [ST][128][64]
+  uint8_t* sV = sK + ST * KV_BYTES;                // [ST][128][64]
   Barriers* bar = reinterpret_cast<Barriers*>(sV + ST * KV_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = frame_of_block(blockIdx.z, a.N), head = blockIdx.y, row0 = blockIdx.x * (QT * BM);
   const float c = a.mode == PAID_PLAIN ? 0.f : a.coef[n];
   const FramePlan plan = make_frame_plan(a.mode, a.fused, n, a.begin_frame, a.end_frame, c);
+  const Segments seg = make_segments(plan);
   const int tiles = (a.L + BN - 1) / BN;
-  const int nsteps[3] = {plan.use0 ? tiles : 0, plan.use1 ? tiles : 0, plan.use2 ? tiles : 0};
-  const int total_steps = nsteps[0] + nsteps[1] + nsteps[2];
+  const int total_steps = seg.count * tiles;
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmQ);
@@ -87,7 +112,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       ptx::mbar_init(&bar->k_full[s], 1); ptx::mbar_init(&bar->k_empty[s], 1);
       ptx::mbar_init(&bar->v_full[s], 1); ptx::mbar_init(&bar->v_empty[s], 1);
     }
-    for (int t = 0; t < QT; ++t) { ptx::mbar_init(&bar->s_full[t], 1); ptx::mbar_init(&bar->p_full[t], BM); }
+    for (int t = 0; t < QT; ++t) {
+      ptx::mbar_init(&bar->s_full[t], 1);
+      ptx::mbar_init(&bar->p_full[t], 4);  // one arrive per softmax warp
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) { ptx::tmem_alloc(&bar->tmem_slot, 512); ptx::tmem_relinquish(); }
@@ -96,17 +124,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   ptx::tc_fence_after();
   const uint32_t tmem = bar->tmem_slot;
 
+  if (warp < 4) {
+  ptx::setmaxnreg_dec<kRegsControl>();
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(&bar->q_full, QT * Q_BYTES);
       for (int t = 0; t < QT; ++t) ptx::tma_load_4d(sQ + t * Q_BYTES, &tmQ, &bar->q_full, 0, head, row0 + t * BM, n);
       int j = 0;
-      for (int slot = 0; slot < 3; ++slot) {
+      for (int g = 0; g < seg.count; ++g) {
+        const int slot = seg.slot[g];
         const CUtensorMap* mk = slot == 0 ? &tmK0 : (slot == 1 ? &tmK1 : &tmK2);
         const CUtensorMap* mv = slot == 0 ? &tmV0 : (slot == 1 ? &tmV1 : &tmV2);
         const int fr = a.per_frame[slot] ? n : 0;
-        for (int i = 0; i < nsteps[slot]; ++i, ++j) {
+        for (int i = 0; i < tiles; ++i, ++j) {
           const int s = j % ST;
           const uint32_t ph = (j / ST) & 1;
           ptx::mbar_wait(&bar->k_empty[s], ph ^ 1);
@@ -123,7 +154,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (ptx::elect_one()) {
       constexpr int fmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
       constexpr uint32_t idesc_qk = ptx::make_idesc(BM, BN, fmt, 0);  // S = Q K^T : both operands K-major
-      constexpr uint32_t idesc_pv = ptx::make_idesc(BM, D, fmt, 1);   // O += P V  : V is N(=d)-contiguous
+      constexpr uint32_t idesc_pv = ptx::make_idesc(BM, D, fmt, 1);   // acc += P V : V is N(=d)-contiguous
       const uint32_t q_addr = ptx::smem_u32(sQ), k_addr = ptx::smem_u32(sK), v_addr = ptx::smem_u32(sV);
       auto issue_qk = [&](int t, int s) {
         const uint64_t qd = ptx::make_smem_desc_sw128(q_addr + t * Q_BYTES, 16, 1024);
@@ -137,9 +168,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       ptx::tc_fence_after();
       for (int t = 0; t < QT; ++t) { issue_qk(t, 0); ptx::tc_commit(&bar->s_full[t]); }
       ptx::tc_commit(&bar->k_empty[0]);
+      bool started[2] = {false, false};  // has stream A / B received a P.V product yet
       int j = 0;
-      for (int slot = 0; slot < 3; ++slot) {
-        for (int i = 0; i < nsteps[slot]; ++i, ++j) {
+      for (int g = 0; g < seg.count; ++g) {
+        const int feeds = seg.feeds[g];
+        for (int i = 0; i < tiles; ++i, ++j) {
           const int s = j % ST, s1 = (j + 1) % ST;
           const bool more = j + 1 < total_steps;
           ptx::mbar_wait(&bar->v_full[s], (j / ST) & 1);
@@ -147,122 +180,171 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int t = 0; t < QT; ++t) {
             ptx::mbar_wait(&bar->p_full[t], j & 1);
             ptx::tc_fence_after();
-            const uint32_t o_t = tmem + TMEM_O + (t * 3 + slot) * D;
             const uint32_t p_t = tmem + TMEM_S + t * BN;
 #pragma unroll
-            for (int k = 0; k < BN / 16; ++k) {
-              // 16 keys per MMA: 8 packed columns of P, 16 rows (2048 B) of the V tile
-              const uint64_t vd = ptx::make_smem_desc_sw128(v_addr + s * KV_BYTES + k * 2048, 16, 1024);
-              ptx::mma_ts(o_t, p_t + k * 8, vd, idesc_pv, (i | k) != 0);
+            for (int st = 0; st < 2; ++st) {
+              if (!(feeds & (1 << st))) continue;
+#if PAID_ABLATE & 8
+              if (started[st]) continue;
+#endif
+              const uint32_t acc = tmem + TMEM_ACC + t * 128 + st * D;
+#pragma unroll
+              for (int k = 0; k < BN / 16; ++k) {
+                // 16 keys per MMA: 8 packed columns of P, 16 rows (2048 B) of the V tile
+                const uint64_t vd = ptx::make_smem_desc_sw128(v_addr + s * KV_BYTES + k * 2048, 16, 1024);
+                ptx::mma_ts(acc, p_t + k * 8, vd, idesc_pv, started[st] || k != 0);
+              }
             }
             if (more) issue_qk(t, s1);
-            ptx::tc_commit(&bar->s_full[t]);  // S_t(j+1) ready; on the last step: all of O_t ready
+            ptx::tc_commit(&bar->s_full[t]);  // S_t(j+1) ready; on the last step: the accumulators are final
           }
+          if (feeds & 1) started[0] = true;
+          if (feeds & 2) started[1] = true;
           ptx::tc_commit(&bar->v_empty[s]);
           if (more) ptx::tc_commit(&bar->k_empty[s1]);
         }
       }
     }
+  }
   } else {
+    ptx::setmaxnreg_inc<kRegsSoftmax>();
     // ================================ softmax warpgroups ==========================
-    const int t = (warp - 2) >> 2;   // Q tile of this warpgroup
+    const int t = (warp - 4) >> 2;   // Q tile of this warpgroup
     const int quad = warp & 3;       // TMEM lane quadrant of this warp
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t s_addr = tmem + lane_base + TMEM_S + t * BN;
+    const uint32_t acc_addr = tmem + lane_base + TMEM_ACC + t * 128;
     const float sl2 = a.scale_log2;
-    float m_slot[3] = {-INFINITY, -INFINITY, -INFINITY}, l_slot[3] = {0.f, 0.f, 0.f};
+    float m_st[2] = {-INFINITY, -INFINITY}, l_st[2] = {0.f, 0.f};  // per stream, m in raw-score units
+    bool started[2] = {false, false};
     int j = 0;
-#pragma unroll
-    for (int slot = 0; slot < 3; ++slot) {
-      float m_ref = -INFINITY, l = 0.f;  // m_ref in raw-score units
-      const uint32_t o_addr = tmem + lane_base + TMEM_O + (t * 3 + slot) * D;
-      for (int i = 0; i < nsteps[slot]; ++i, ++j) {
+    for (int g = 0; g < seg.count; ++g) {
+      const int feeds = seg.feeds[g];
+      const int primary = (feeds & 1) ? 0 : 1;   // streams fed together have identical statistics
+      float m_ref = m_st[primary], l = l_st[primary];
+      const bool fresh = !started[primary];
+      for (int i = 0; i < tiles; ++i, ++j) {
         ptx::mbar_wait(&bar->s_full[t], j & 1);
         ptx::tc_fence_after();
-        uint32_t sr[2][32];
-        ptx::tmem_ld32(s_addr, sr[0]);
-        ptx::tmem_ld32(s_addr + 32, sr[1]);
-        ptx::tmem_wait_ld();
-        const int valid = a.L - i * BN;  // keys of this tile that exist
-        if (valid < BN) {
+        uint32_t sr[4][32];
+#if PAID_ABLATE & 16
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) sr[h][e] = __float_as_uint((float)(e + j) * 0.01f);
+#else
+#pragma unroll
+        for (int h = 0; h < 4; ++h) ptx::tmem_ld32(s_addr + h * 32, sr[h]);
+        ptx::tmem_wait_ld();
+#endif
+        const int valid = a.L - i * BN;  // keys of this tile that exist
+        if (valid < BN) {                // ragged last tile only (kept a real branch by the asm statement)
+          asm volatile("" ::: "memory");
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
 #pragma unroll
             for (int e = 0; e < 32; ++e)
               if (h * 32 + e >= valid) sr[h][e] = __float_as_uint(-INFINITY);
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#if PAID_ABLATE & 4
+        mx0 = __uint_as_float(sr[0][0]);
+#else
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sr[0][e]), __uint_as_float(sr[1][e])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sr[0][e + 1]), __uint_as_float(sr[1][e + 1])));
-          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sr[0][e + 2]), __uint_as_float(sr[1][e + 2])));
-          mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sr[0][e + 3]), __uint_as_float(sr[1][e + 3])));
+        for (int e = 0; e < 32; ++e) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[0][e]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[1][e]));
+          mx2 = fmaxf(mx2, __uint_as_float(sr[2][e]));
+          mx3 = fmaxf(mx3, __uint_as_float(sr[3][e]));
         }
+#endif
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        if (i == 0) {
-          m_ref = mx;  // fresh accumulator: the first P.V of a slot overwrites O
+        if (i == 0 && fresh) {
+          m_ref = mx;  // fresh accumulators: the first P.V of a stream overwrites them
         } else {
           const bool grow = (mx - m_ref) * sl2 > kRescaleThreshold;
           if (__any_sync(0xffffffffu, grow)) {
-            // O_{t,slot} is quiescent here: s_full fired after every earlier MMA of this tile completed
+            // the accumulators are quiescent here: s_full fired after every earlier MMA of this tile completed
             const float m_new = grow ? mx : m_ref;
-            const float alpha = exp2f((m_ref - m_new) * sl2);
+            const float alpha = ptx::ex2((m_ref - m_new) * sl2);
             l *= alpha;
             m_ref = m_new;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              uint32_t o[32];
-              ptx::tmem_ld32(o_addr + h * 32, o);
-              ptx::tmem_wait_ld();
+            for (int st = 0; st < 2; ++st) {
+              if (!(feeds & (1 << st))) continue;
 #pragma unroll
-              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-              ptx::tmem_st32(o_addr + h * 32, o);
+              for (int h = 0; h < 2; ++h) {
+                uint32_t o[32];
+                ptx::tmem_ld32(acc_addr + st * D + h * 32, o);
+                ptx::tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                  const float2 r = ptx::mul2(make_float2(__uint_as_float(o[e]), __uint_as_float(o[e + 1])),
+                                             make_float2(alpha, alpha));
+                  o[e] = __float_as_uint(r.x); o[e + 1] = __float_as_uint(r.y);
+                }
+                ptx::tmem_st32(acc_addr + st * D + h * 32, o);
+              }
             }
           }
         }
         const float neg = -m_ref * sl2;
-        uint32_t pk[32];
-        float sum0 = 0.f, sum1 = 0.f;
+        const float2 sl2v = make_float2(sl2, sl2), negv = make_float2(neg, neg);
+        float2 sumA = make_float2(0.f, 0.f), sumB = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 4; ++h) {
+          uint32_t pk[16];
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float p0 = exp2f(fmaf(__uint_as_float(sr[h][e]), sl2, neg));
-            const float p1 = exp2f(fmaf(__uint_as_float(sr[h][e + 1]), sl2, neg));
-            sum0 += p0; sum1 += p1;
-            pk[h * 16 + e / 2] = pack2<T>(p0, p1);
+          for (int e = 0; e < 32; e += 4) {
+            // two packed fp32x2 FMAs (x * scale*log2e - max), four MUFU.EX2, two packed adds, two packed converts
+            float2 x0 = ptx::fma2(make_float2(__uint_as_float(sr[h][e]), __uint_as_float(sr[h][e + 1])), sl2v, negv);
+            float2 x1 = ptx::fma2(make_float2(__uint_as_float(sr[h][e + 2]), __uint_as_float(sr[h][e + 3])), sl2v, negv);
+#if PAID_ABLATE & 1
+            x0.x *= 1e-3f; x0.y *= 1e-3f; x1.x *= 1e-3f; x1.y *= 1e-3f;
+#else
+            x0.x = ptx::ex2(x0.x); x0.y = ptx::ex2(x0.y); x1.x = ptx::ex2(x1.x); x1.y = ptx::ex2(x1.y);
+#endif
+            sumA = ptx::add2(sumA, x0);
+            sumB = ptx::add2(sumB, x1);
+            pk[e / 2] = pack2<T>(x0.x, x0.y);
+            pk[e / 2 + 1] = pack2<T>(x1.x, x1.y);
           }
-        l += sum0 + sum1;
-        ptx::tmem_st32(s_addr, pk);  // P_t over the low half of S_t
+#if PAID_ABLATE & 2
+          if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) ptx::tmem_st16(s_addr + h * 16, pk);
+#else
+          ptx::tmem_st16(s_addr + h * 16, pk);  // P_t over the low half of S_t (all of S_t is in registers)
+#endif
+        }
+        l += (sumA.x + sumA.y) + (sumB.x + sumB.y);
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&bar->p_full[t]);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar->p_full[t]);
       }
-      m_slot[slot] = m_ref * sl2;
-      l_slot[slot] = l;
+#pragma unroll
+      for (int st = 0; st < 2; ++st)
+        if (feeds & (1 << st)) { m_st[st] = m_ref; l_st[st] = l; started[st] = true; }
     }
-    // ---- epilogue: merge the slots, alpha-lerp, write the head's 64 output channels of this row ----
+    // ---- epilogue: out = wA * accA / lA + wB * accB / lB for this row's 64 channels of the head ----
     ptx::mbar_wait(&bar->s_full[t], j & 1);
     ptx::tc_fence_after();
-    float cf[3];
-    merge_coefficients(plan, m_slot[0], l_slot[0], m_slot[1], l_slot[1], m_slot[2], l_slot[2], cf[0], cf[1], cf[2]);
+    const float cf[2] = {seg.a_active ? plan.wA / l_st[0] : 0.f, seg.b_active ? plan.wB / l_st[1] : 0.f};
+    const bool active[2] = {seg.a_active, seg.b_active};
     const int row = row0 + t * BM + quad * 32 + lane;
     T* dst = (T*)a.out + ((long long)n * a.S + row) * (a.heads * D) + head * D;
-    const bool used[3] = {plan.use0, plan.use1, plan.use2};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float acc[32];
 #pragma unroll
       for (int e = 0; e < 32; ++e) acc[e] = 0.f;
 #pragma unroll
-      for (int slot = 0; slot < 3; ++slot) {
-        if (!used[slot]) continue;  // CTA-uniform
+      for (int st = 0; st < 2; ++st) {
+        if (!active[st]) continue;  // CTA-uniform
         uint32_t o[32];
-        ptx::tmem_ld32(tmem + lane_base + TMEM_O + (t * 3 + slot) * D + h * 32, o);
+        ptx::tmem_ld32(acc_addr + st * D + h * 32, o);
         ptx::tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] = fmaf(cf[slot], __uint_as_float(o[e]), acc[e]);
+        for (int e = 0; e < 32; ++e) acc[e] = fmaf(cf[st], __uint_as_float(o[e]), acc[e]);
       }
       if (row < a.S) {
 #pragma unroll
