@@ -12,20 +12,20 @@
 // accumulators; endpoint K/V are read once per CTA and never replicated or concatenated.
 //
 // Work decomposition: one CTA per (frame, head, 256 query rows) = two 128-row Q tiles sharing every K/V tile.
-//   warp 0        TMA producer: Q tiles once, then K / V tiles (128 keys) into a 4-stage shared-memory ring
+//   warp 0        TMA producer: Q tiles once, then K / V tiles (64 keys) into an 8-stage shared-memory ring
 //   warp 1        tcgen05.mma issuer: S_t = Q_t K^T (SS), acc_{t,stream} += P_t V (A operand P from TMEM)
-//   warps 2-5     softmax warpgroup of Q tile 0 (one thread per query row)
-//   warps 6-9     softmax warpgroup of Q tile 1
-// TMEM (512 columns): S_t at 128 t (P_t aliases its low 64 columns as packed 16-bit), acc_{t,stream} at
-// 256 + 128 t + 64 stream.
+//   warps 2-3     idle (they only give their registers away)
+//   warps 4-7     softmax warpgroup of Q tile 0 (one thread per query row)
+//   warps 8-11    softmax warpgroup of Q tile 1
+// The score tile of each Q tile is DOUBLE-BUFFERED in TMEM: S_t(j+2) = Q_t K(j+2)^T is issued right after
+// P_t(j) V(j), so the scores of the next step are ready while the softmax warps still work on the current
+// one and the exp-bound softmax never waits for the tensor core.
+// TMEM (512 columns): S_{t,b} at 64 (2 t + b) (P_{t,b} aliases its low 32 columns as packed 16-bit),
+// acc_{t,stream} at 256 + 128 t + 64 stream.
 #include <type_traits>
 
 #include "paid_common.cuh"
 #include "sm100_ptx.cuh"
-
-#ifndef PAID_ABLATE
-#define PAID_ABLATE 0  // experiments only: 1 no MUFU, 2 no P store, 4 no max, 8 no P.V MMA, 16 no S load
-#endif
 
 namespace paid {
 namespace {
@@ -33,8 +33,8 @@ namespace {
 constexpr int D = 64;            // head_dim
 constexpr int BM = 128;          // rows per Q tile
 constexpr int QT = 2;            // Q tiles per CTA
-constexpr int BN = 128;          // keys per step
-constexpr int ST = 4;            // K/V ring stages
+constexpr int BN = 64;           // keys per step
+constexpr int ST = 8;            // K/V ring stages
 constexpr int Q_BYTES = BM * D * 2;    // 16 KB
 constexpr int KV_BYTES = BN * D * 2;   // 16 KB
 constexpr int SMEM_BYTES = 1024 + QT * Q_BYTES + ST * 2 * KV_BYTES + 512;
@@ -54,7 +54,7 @@ struct TcArgs {
 struct Barriers {
   uint64_t q_full;
   uint64_t k_full[ST], k_empty[ST], v_full[ST], v_empty[ST];
-  uint64_t s_full[QT], p_full[QT];
+  uint64_t s_full[QT][2], p_full[QT][2], pv_done[QT];
   uint32_t tmem_slot;
 };
 
@@ -113,8 +113,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       ptx::mbar_init(&bar->v_full[s], 1); ptx::mbar_init(&bar->v_empty[s], 1);
     }
     for (int t = 0; t < QT; ++t) {
-      ptx::mbar_init(&bar->s_full[t], 1);
-      ptx::mbar_init(&bar->p_full[t], 4);  // one arrive per softmax warp
+      for (int b = 0; b < 2; ++b) {
+        ptx::mbar_init(&bar->s_full[t][b], 1);
+        ptx::mbar_init(&bar->p_full[t][b], 4);  // one arrive per softmax warp
+      }
+      ptx::mbar_init(&bar->pv_done[t], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -156,37 +159,37 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       constexpr uint32_t idesc_qk = ptx::make_idesc(BM, BN, fmt, 0);  // S = Q K^T : both operands K-major
       constexpr uint32_t idesc_pv = ptx::make_idesc(BM, D, fmt, 1);   // acc += P V : V is N(=d)-contiguous
       const uint32_t q_addr = ptx::smem_u32(sQ), k_addr = ptx::smem_u32(sK), v_addr = ptx::smem_u32(sV);
-      auto issue_qk = [&](int t, int s) {
+      auto issue_qk = [&](int t, int b, int s) {
         const uint64_t qd = ptx::make_smem_desc_sw128(q_addr + t * Q_BYTES, 16, 1024);
         const uint64_t kd = ptx::make_smem_desc_sw128(k_addr + s * KV_BYTES, 16, 1024);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          ptx::mma_ss(tmem + TMEM_S + t * BN, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+          ptx::mma_ss(tmem + TMEM_S + (t * 2 + b) * BN, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
       };
+      // prologue: scores of steps 0 and 1
       ptx::mbar_wait(&bar->q_full, 0);
-      ptx::mbar_wait(&bar->k_full[0], 0);
-      ptx::tc_fence_after();
-      for (int t = 0; t < QT; ++t) { issue_qk(t, 0); ptx::tc_commit(&bar->s_full[t]); }
-      ptx::tc_commit(&bar->k_empty[0]);
+      for (int jj = 0; jj < 2 && jj < total_steps; ++jj) {
+        ptx::mbar_wait(&bar->k_full[jj], 0);
+        ptx::tc_fence_after();
+        for (int t = 0; t < QT; ++t) { issue_qk(t, jj, jj); ptx::tc_commit(&bar->s_full[t][jj]); }
+        ptx::tc_commit(&bar->k_empty[jj]);
+      }
       bool started[2] = {false, false};  // has stream A / B received a P.V product yet
       int j = 0;
       for (int g = 0; g < seg.count; ++g) {
         const int feeds = seg.feeds[g];
         for (int i = 0; i < tiles; ++i, ++j) {
-          const int s = j % ST, s1 = (j + 1) % ST;
-          const bool more = j + 1 < total_steps;
+          const int s = j % ST, s2 = (j + 2) % ST, b = j & 1;
+          const bool more = j + 2 < total_steps;
           ptx::mbar_wait(&bar->v_full[s], (j / ST) & 1);
-          if (more) ptx::mbar_wait(&bar->k_full[s1], ((j + 1) / ST) & 1);
+          if (more) ptx::mbar_wait(&bar->k_full[s2], ((j + 2) / ST) & 1);
           for (int t = 0; t < QT; ++t) {
-            ptx::mbar_wait(&bar->p_full[t], j & 1);
+            ptx::mbar_wait(&bar->p_full[t][b], (j >> 1) & 1);
             ptx::tc_fence_after();
-            const uint32_t p_t = tmem + TMEM_S + t * BN;
+            const uint32_t p_t = tmem + TMEM_S + (t * 2 + b) * BN;
 #pragma unroll
             for (int st = 0; st < 2; ++st) {
               if (!(feeds & (1 << st))) continue;
-#if PAID_ABLATE & 8
-              if (started[st]) continue;
-#endif
               const uint32_t acc = tmem + TMEM_ACC + t * 128 + st * D;
 #pragma unroll
               for (int k = 0; k < BN / 16; ++k) {
@@ -195,13 +198,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 ptx::mma_ts(acc, p_t + k * 8, vd, idesc_pv, started[st] || k != 0);
               }
             }
-            if (more) issue_qk(t, s1);
-            ptx::tc_commit(&bar->s_full[t]);  // S_t(j+1) ready; on the last step: the accumulators are final
+            ptx::tc_commit(&bar->pv_done[t]);     // accumulators of tile t include step j
+            if (more) {                            // S_{t,b} is free again (in-order after the P.V above)
+              issue_qk(t, b, s2);
+              ptx::tc_commit(&bar->s_full[t][b]);  // scores of step j + 2
+            }
           }
           if (feeds & 1) started[0] = true;
           if (feeds & 2) started[1] = true;
           ptx::tc_commit(&bar->v_empty[s]);
-          if (more) ptx::tc_commit(&bar->k_empty[s1]);
+          if (more) ptx::tc_commit(&bar->k_empty[s2]);
         }
       }
     }
@@ -212,7 +218,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int t = (warp - 4) >> 2;   // Q tile of this warpgroup
     const int quad = warp & 3;       // TMEM lane quadrant of this warp
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const uint32_t s_addr = tmem + lane_base + TMEM_S + t * BN;
+    const uint32_t s_base = tmem + lane_base + TMEM_S + t * 2 * BN;
     const uint32_t acc_addr = tmem + lane_base + TMEM_ACC + t * 128;
     const float sl2 = a.scale_log2;
     float m_st[2] = {-INFINITY, -INFINITY}, l_st[2] = {0.f, 0.f};  // per stream, m in raw-score units
@@ -224,47 +230,41 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       float m_ref = m_st[primary], l = l_st[primary];
       const bool fresh = !started[primary];
       for (int i = 0; i < tiles; ++i, ++j) {
-        ptx::mbar_wait(&bar->s_full[t], j & 1);
+        const int b = j & 1;
+        const uint32_t s_addr = s_base + b * BN;
+        ptx::mbar_wait(&bar->s_full[t][b], (j >> 1) & 1);
         ptx::tc_fence_after();
-        uint32_t sr[4][32];
-#if PAID_ABLATE & 16
+        uint32_t sr[2][32];
 #pragma unroll
-        for (int h = 0; h < 4; ++h)
-#pragma unroll
-          for (int e = 0; e < 32; ++e) sr[h][e] = __float_as_uint((float)(e + j) * 0.01f);
-#else
-#pragma unroll
-        for (int h = 0; h < 4; ++h) ptx::tmem_ld32(s_addr + h * 32, sr[h]);
+        for (int h = 0; h < 2; ++h) ptx::tmem_ld32(s_addr + h * 32, sr[h]);
         ptx::tmem_wait_ld();
-#endif
         const int valid = a.L - i * BN;  // keys of this tile that exist
         if (valid < BN) {                // ragged last tile only (kept a real branch by the asm statement)
           asm volatile("" ::: "memory");
 #pragma unroll
-          for (int h = 0; h < 4; ++h)
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int e = 0; e < 32; ++e)
               if (h * 32 + e >= valid) sr[h][e] = __float_as_uint(-INFINITY);
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#if PAID_ABLATE & 4
-        mx0 = __uint_as_float(sr[0][0]);
-#else
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
+        for (int e = 0; e < 32; e += 2) {
           mx0 = fmaxf(mx0, __uint_as_float(sr[0][e]));
-          mx1 = fmaxf(mx1, __uint_as_float(sr[1][e]));
-          mx2 = fmaxf(mx2, __uint_as_float(sr[2][e]));
-          mx3 = fmaxf(mx3, __uint_as_float(sr[3][e]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[0][e + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sr[1][e]));
+          mx3 = fmaxf(mx3, __uint_as_float(sr[1][e + 1]));
         }
-#endif
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
         if (i == 0 && fresh) {
           m_ref = mx;  // fresh accumulators: the first P.V of a stream overwrites them
         } else {
           const bool grow = (mx - m_ref) * sl2 > kRescaleThreshold;
           if (__any_sync(0xffffffffu, grow)) {
-            // the accumulators are quiescent here: s_full fired after every earlier MMA of this tile completed
+            // rare: wait until the P.V of step j-1 has landed, then the accumulators are quiescent (the P.V of
+            // step j cannot be issued before this thread publishes P(j))
+            ptx::mbar_wait(&bar->pv_done[t], (j - 1) & 1);
+            ptx::tc_fence_after();
             const float m_new = grow ? mx : m_ref;
             const float alpha = ptx::ex2((m_ref - m_new) * sl2);
             l *= alpha;
@@ -292,41 +292,37 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const float2 sl2v = make_float2(sl2, sl2), negv = make_float2(neg, neg);
         float2 sumA = make_float2(0.f, 0.f), sumB = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
+        for (int h = 0; h < 2; ++h) {
           uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
             // two packed fp32x2 FMAs (x * scale*log2e - max), four MUFU.EX2, two packed adds, two packed converts
             float2 x0 = ptx::fma2(make_float2(__uint_as_float(sr[h][e]), __uint_as_float(sr[h][e + 1])), sl2v, negv);
             float2 x1 = ptx::fma2(make_float2(__uint_as_float(sr[h][e + 2]), __uint_as_float(sr[h][e + 3])), sl2v, negv);
-#if PAID_ABLATE & 1
-            x0.x *= 1e-3f; x0.y *= 1e-3f; x1.x *= 1e-3f; x1.y *= 1e-3f;
-#else
             x0.x = ptx::ex2(x0.x); x0.y = ptx::ex2(x0.y); x1.x = ptx::ex2(x1.x); x1.y = ptx::ex2(x1.y);
-#endif
             sumA = ptx::add2(sumA, x0);
             sumB = ptx::add2(sumB, x1);
             pk[e / 2] = pack2<T>(x0.x, x0.y);
             pk[e / 2 + 1] = pack2<T>(x1.x, x1.y);
           }
-#if PAID_ABLATE & 2
-          if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) ptx::tmem_st16(s_addr + h * 16, pk);
-#else
-          ptx::tmem_st16(s_addr + h * 16, pk);  // P_t over the low half of S_t (all of S_t is in registers)
-#endif
+          ptx::tmem_st16(s_addr + h * 16, pk);  // P over the low half of this S buffer (all of S is in registers)
         }
         l += (sumA.x + sumA.y) + (sumB.x + sumB.y);
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar->p_full[t]);
+        if (lane == 0) ptx::mbar_arrive(&bar->p_full[t][b]);
       }
 #pragma unroll
       for (int st = 0; st < 2; ++st)
         if (feeds & (1 << st)) { m_st[st] = m_ref; l_st[st] = l; started[st] = true; }
     }
     // ---- epilogue: out = wA * accA / lA + wB * accB / lB for this row's 64 channels of the head ----
-    ptx::mbar_wait(&bar->s_full[t], j & 1);
+    // All P.V products of this tile must have landed.  pv_done completes once per step and a parity wait can
+    // only tell the current phase from the previous one, so wait for the last two completions in order (the
+    // scores of the last step being ready already implies every completion before those two).
+    if (j >= 2) ptx::mbar_wait(&bar->pv_done[t], (j - 2) & 1);
+    ptx::mbar_wait(&bar->pv_done[t], (j - 1) & 1);
     ptx::tc_fence_after();
     const float cf[2] = {seg.a_active ? plan.wA / l_st[0] : 0.f, seg.b_active ? plan.wB / l_st[1] : 0.f};
     const bool active[2] = {seg.a_active, seg.b_active};

@@ -199,3 +199,39 @@ def test_pipeline_frame_sharding_equals_single_batch(cabi):
     # a single-rank shard covers all frames and goes through project_endpoints + kv_ext
     one = InterpolationPipeline(net, shard=FrameShard(0, 1, 5)).interpolate(**args)
     check(one.float().cpu(), full.float().cpu(), "world-size-1 shard", rel=2e-3)
+
+
+def test_core_growing_logits_exercise_rescale(cabi):
+    """Keys whose scores keep growing along the sequence force the online-softmax rescale of the accumulators
+    (running max rising by far more than the lazy threshold) in every segment; also peaked (near one-hot) rows."""
+    N, S, L, h, d = 4, 256, 640, 2, 64
+    torch.manual_seed(11)
+    q = torch.randn(N, S, h * d)
+    k = torch.randn(N, L, h * d) * torch.linspace(0.2, 6.0, L).view(1, L, 1)
+    v = torch.randn(N, L, h * d)
+    coef = O.coefficients(N, 2, 2)
+    ends = tuple(rounded(t) for t in (k[0], v[0], k[-1], v[-1]))
+    for m, fused in MODES + [("plain", False)]:
+        mode = O.MODE_NAMES[m]
+        out = cabi.attn_core(dev(q), dev(k), dev(v), coef.cuda(), h, mode, fused)
+        torch.cuda.synchronize()
+        ref = O._direct_core(rounded(q), rounded(k), rounded(v), ends, coef, mode, fused, d ** -0.5, h)
+        check(out.float().cpu(), ref, ("growing logits", m, fused), rel=2e-3)
+        gen = cabi.attn_core(dev(q), dev(k), dev(v), coef.cuda(), h, mode, fused, flags=cabi.FLAG_GENERIC_KERNELS)
+        check(out.float().cpu(), gen.float().cpu(), ("growing logits vs generic", m, fused), rel=2e-3)
+
+
+def test_core_is_deterministic_under_repetition(cabi):
+    """Race detector: the same launch repeated must be bit-identical (SDXL 32x32 geometry, all modes)."""
+    N, S, h, d = 7, 1024, 20, 64
+    torch.manual_seed(3)
+    q, k, v = (torch.randn(N, S, h * d, device="cuda").half() for _ in range(3))
+    coef = O.coefficients(N, 4, 4).cuda()
+    for m, fused in MODES + [("plain", False)]:
+        mode = O.MODE_NAMES[m]
+        first = cabi.attn_core(q, k, v, coef, h, mode, fused).clone()
+        for _ in range(8):
+            again = cabi.attn_core(q, k, v, coef, h, mode, fused)
+            assert torch.equal(first, again), (m, fused)
+    gen = cabi.attn_core(q, k, v, coef, h, O.MODE_OUTER, True, flags=cabi.FLAG_GENERIC_KERNELS)
+    check(cabi.attn_core(q, k, v, coef, h, O.MODE_OUTER, True).float().cpu(), gen.float().cpu(), "vs generic", rel=1e-3)
