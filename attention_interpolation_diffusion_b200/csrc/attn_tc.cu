@@ -54,7 +54,7 @@ struct TcArgs {
 struct Barriers {
   uint64_t q_full;
   uint64_t k_full[ST], k_empty[ST], v_full[ST], v_empty[ST];
-  uint64_t s_full[QT][2], p_full[QT][2], pv_done[QT];
+  uint64_t s_full[QT][2], p_full[QT][2], pv_done[QT], acc_final[QT];
   uint32_t tmem_slot;
 };
 
@@ -118,6 +118,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         ptx::mbar_init(&bar->p_full[t][b], 4);  // one arrive per softmax warp
       }
       ptx::mbar_init(&bar->pv_done[t], 1);
+      ptx::mbar_init(&bar->acc_final[t], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -199,6 +200,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               }
             }
             ptx::tc_commit(&bar->pv_done[t]);     // accumulators of tile t include step j
+            if (j + 1 == total_steps) ptx::tc_commit(&bar->acc_final[t]);  // single-use: everything has landed
             if (more) {                            // S_{t,b} is free again (in-order after the P.V above)
               issue_qk(t, b, s2);
               ptx::tc_commit(&bar->s_full[t][b]);  // scores of step j + 2
@@ -318,11 +320,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (feeds & (1 << st)) { m_st[st] = m_ref; l_st[st] = l; started[st] = true; }
     }
     // ---- epilogue: out = wA * accA / lA + wB * accB / lB for this row's 64 channels of the head ----
-    // All P.V products of this tile must have landed.  pv_done completes once per step and a parity wait can
-    // only tell the current phase from the previous one, so wait for the last two completions in order (the
-    // scores of the last step being ready already implies every completion before those two).
-    if (j >= 2) ptx::mbar_wait(&bar->pv_done[t], (j - 2) & 1);
-    ptx::mbar_wait(&bar->pv_done[t], (j - 1) & 1);
+    // All P.V products of this tile must have landed: a dedicated single-phase barrier (pv_done completes once
+    // per step, and a parity wait cannot be used on a barrier whose phases this thread has skipped).
+    ptx::mbar_wait(&bar->acc_final[t], 0);
     ptx::tc_fence_after();
     const float cf[2] = {seg.a_active ? plan.wA / l_st[0] : 0.f, seg.b_active ? plan.wB / l_st[1] : 0.f};
     const bool active[2] = {seg.a_active, seg.b_active};

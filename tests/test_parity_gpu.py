@@ -235,3 +235,18 @@ def test_core_is_deterministic_under_repetition(cabi):
             assert torch.equal(first, again), (m, fused)
     gen = cabi.attn_core(q, k, v, coef, h, O.MODE_OUTER, True, flags=cabi.FLAG_GENERIC_KERNELS)
     check(cabi.attn_core(q, k, v, coef, h, O.MODE_OUTER, True).float().cpu(), gen.float().cpu(), "vs generic", rel=1e-3)
+
+
+def test_core_stress_many_launches(cabi):
+    """Rare-interleaving detector: thousands of back-to-back launches (a protocol deadlock trips the in-kernel
+    watchdog and surfaces as a CUDA error at the synchronize)."""
+    torch.manual_seed(5)
+    N, coef = 7, O.coefficients(7, 4, 4).cuda()
+    shapes = [(1024, 1024, 20), (1024, 77, 20), (4096, 77, 10)]
+    data = [tuple(torch.randn(N, T, h * 64, device="cuda").half() for T in (S, L, L)) + (h,) for S, L, h in shapes]
+    for it in range(700):
+        q, k, v, h = data[it % len(data)]
+        mode, fused = ((O.MODE_OUTER, True), (O.MODE_PLAIN, False), (O.MODE_INNER, True))[it % 3]
+        out = cabi.attn_core(q, k, v, coef, h, mode, fused)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
