@@ -64,11 +64,50 @@ def slerp(v0: torch.Tensor, v1: torch.Tensor, t: float, threshold: float = 0.999
     return torch.where(linear, torch.lerp(v0, v1, t), sph)
 
 
+class _GraphedForward:
+    """One UNet forward (fixed processor state and shapes) captured into a CUDA graph.  The ~2400 kernel launches
+    of a forward otherwise cost ~100 ms of host time, more than the GPU needs to execute them."""
+
+    def __init__(self, unet, sample, t, ctx, added):
+        from . import _cabi
+        dev = sample.device
+        self.sample, self.ctx = sample.clone(), ctx.clone()
+        self.t = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.added = None if added is None else {k: v.clone() for k, v in added.items()}
+        self.t.fill_(float(t))
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):      # warm-up outside capture: cuDNN autotune, lazy init, coef upload, workspace
+            for _ in range(2):
+                unet(self.sample, self.t, self.ctx, self.added)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.workspace = _cabi._workspaces.get(dev)      # keep the scratch buffer the graph points into alive
+        n0 = _cabi.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = unet(self.sample, self.t, self.ctx, self.added)
+        self.launches = _cabi.launch_count() - n0       # libpaid_attn kernels inside one replay
+
+    def __call__(self, sample, t, ctx, added):
+        self.sample.copy_(sample)
+        self.ctx.copy_(ctx)
+        self.t.fill_(float(t))
+        if added is not None:
+            for k, v in added.items():
+                self.added[k].copy_(v)
+        self.graph.replay()
+        return self.out
+
+
 class InterpolationPipeline:
-    def __init__(self, unet: UNetHarness, shard: Optional[FrameShard] = None):
+    def __init__(self, unet: UNetHarness, shard: Optional[FrameShard] = None, use_cuda_graphs: bool = True):
         self.unet = unet
         self.scheduler = DDIMScheduler()
         self.shard = shard
+        self.use_cuda_graphs = use_cuda_graphs
+        self._graphs: dict = {}
+        self.graph_kernel_launches = 0     # libpaid_attn kernels executed through graph replays
         self.load_aid()
 
     # ---- processor install / toggle (sdxl:1066-1136) ---------------------------------------------
@@ -87,6 +126,7 @@ class InterpolationPipeline:
             else:
                 attn_procs[name] = old
         self.unet.set_attn_processor(attn_procs)
+        self._graphs.clear()               # captured forwards bake the processor objects in
 
     def activate_aid(self, it: float):
         for name, proc in self.unet.attn_processors.items():
@@ -112,18 +152,35 @@ class InterpolationPipeline:
         self.scheduler.set_timesteps(num_inference_steps)
         warmup_steps = int(num_inference_steps * warmup_ratio)
         latents = latents * self.scheduler.init_noise_sigma
+        graphs = (self.use_cuda_graphs and latents.is_cuda and
+                  (self.shard is None or self.shard.world_size == 1))
         for i, t in enumerate(self.scheduler.timesteps.tolist()):
             model_in = self.scheduler.scale_model_input(latents, t)
-            if i < warmup_steps:
-                self.set_coefs(coef)
-            else:
-                self.deactivate_aid()
-            noise_text = self.unet(model_in, t, cond, added_cond)
-            self.deactivate_aid()
-            noise_uncond = self.unet(model_in, t, uncond, added_uncond)
+            noise_text = self._forward(i < warmup_steps, coef, model_in, t, cond, added_cond, graphs)
+            if graphs:
+                noise_text = noise_text.clone()      # the next replay may reuse the same static output
+            noise_uncond = self._forward(False, coef, model_in, t, uncond, added_uncond, graphs)
             noise = noise_uncond + guidance_scale * (noise_text - noise_uncond)
             latents = self.scheduler.step(noise, t, latents)
         return latents
+
+    def _set_mode(self, aid: bool, coef):
+        if aid:
+            self.set_coefs(coef)      # AID on (conditional pass of the first warmup_steps steps, sdxl:2245-2246)
+        else:
+            self.deactivate_aid()     # stock attention (sdxl:2248, 2272)
+
+    def _forward(self, aid: bool, coef, sample, t, ctx, added, graphs: bool):
+        if not graphs:
+            self._set_mode(aid, coef)
+            return self.unet(sample, t, ctx, added)
+        key = (aid, tuple(float(c) for c in coef) if aid else None, tuple(sample.shape), tuple(ctx.shape), sample.dtype)
+        g = self._graphs.get(key)
+        if g is None:
+            self._set_mode(aid, coef)
+            g = self._graphs[key] = _GraphedForward(self.unet, sample, t, ctx, added)
+        self.graph_kernel_launches += g.launches
+        return g(sample, t, ctx, added)
 
     def _added(self, n, text_embeds, device, dtype):
         if not self.unet.cfg.text_time:
