@@ -50,6 +50,8 @@ class PaidCoreParams(C.Structure):
         ("scale", C.c_float), ("begin_frame", C.c_int32), ("end_frame", C.c_int32),
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("kv_ext", C.c_void_p), ("coef", C.c_void_p),
         ("out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
+        ("accumulate", C.c_int32), ("out_scale", C.c_float), ("out_frame_scale", C.c_void_p),
+        ("kv_broadcast", C.c_int32),
     ]
 
 
@@ -221,10 +223,12 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 
 
 def attn_core(q, k, v, coef, heads: int, mode: int, fused: bool, scale=None, begin_frame=None, end_frame=None,
-              kv_ext=None, flags: int = 0) -> torch.Tensor:
-    """Attention on projected tensors through ``paid_attn_core``: q (N,S,C), k/v (N,L,C)."""
+              kv_ext=None, flags: int = 0, out=None, accumulate: bool = False, out_scale: float = 1.0,
+              out_frame_scale=None, kv_broadcast: bool = False) -> torch.Tensor:
+    """Attention on projected tensors through ``paid_attn_core``: q (N,S,C), k/v (N,L,C) (or (1,L,C) with
+    kv_broadcast).  ``out`` + ``accumulate`` add ``out_scale * out_frame_scale[n] * attention`` to an existing result."""
     lib = load_library()
-    _dev_check(q, k, v, coef, kv_ext)
+    _dev_check(q, k, v, coef, kv_ext, out, out_frame_scale)
     N, S, Cdim = q.shape
     p = PaidCoreParams()
     p.struct_size = C.sizeof(PaidCoreParams)
@@ -234,7 +238,10 @@ def attn_core(q, k, v, coef, heads: int, mode: int, fused: bool, scale=None, beg
     p.scale = float((Cdim // heads) ** -0.5 if scale is None else scale)
     p.begin_frame = 0 if begin_frame is None else begin_frame
     p.end_frame = N - 1 if end_frame is None else end_frame
-    out = torch.empty_like(q)
+    if accumulate and out is None:
+        raise RuntimeError("accumulate needs an existing out tensor")
+    out = torch.empty_like(q) if out is None else out
+    p.accumulate, p.out_scale, p.out_frame_scale, p.kv_broadcast = int(accumulate), float(out_scale), _ptr(out_frame_scale), int(kv_broadcast)
     p.q, p.k, p.v, p.kv_ext, p.coef, p.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), _ptr(kv_ext), _ptr(coef), out.data_ptr()
     need = lib.paid_attn_core_workspace_bytes(C.byref(p))
     if need:

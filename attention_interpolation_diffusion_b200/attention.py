@@ -27,6 +27,49 @@ class PaidAttnProcessor:
             attn.to_out[0].weight, attn.to_out[0].bias, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale)
 
 
+def split_ip_states(encoder_hidden_states, num_tokens, batch):
+    """(text, image tokens) from the forms the reference accepts (interpolation.py:254-266): a tuple
+    ``(text, [ip])`` or one tensor with the image tokens appended.  Image tokens may come with the reference's 3x
+    row repetition (rows [s,s,s,t,t,t,e,e,e] for a batch of 3, sdxl:2146-2185): un-repeated like its ``[::3]``."""
+    if isinstance(encoder_hidden_states, tuple):
+        text, ip = encoder_hidden_states
+        ip = ip[0] if isinstance(ip, (list, tuple)) else ip
+    else:
+        end = encoder_hidden_states.shape[1] - num_tokens[0]
+        text, ip = encoder_hidden_states[:, :end, :], encoder_hidden_states[:, end:, :]
+    if ip.ndim == 4:                      # (B, num_images=1, T, Cc) of newer diffusers
+        ip = ip.reshape(ip.shape[0], -1, ip.shape[-1])
+    if ip.shape[0] == 3 * batch:
+        ip = ip[::3]
+    if ip.shape[0] != batch:
+        raise ValueError(f"image tokens for {ip.shape[0]} frames, batch of {batch}")
+    return text.contiguous(), ip.contiguous()
+
+
+class PaidIPAdapterAttnProcessor(nn.Module):
+    """Stock IP-Adapter attention (role of diffusers ``IPAdapterAttnProcessor2_0``, the ``ip_attn`` the reference
+    wraps at pipeline_interpolated_sdxl.py:1110-1126): plain text attention + scale * plain image-token attention."""
+
+    def __init__(self, hidden_size: int, cross_attention_dim: int, num_tokens=(4,), scale=1.0):
+        super().__init__()
+        self.num_tokens = tuple(num_tokens)
+        self.scale = [scale] if not isinstance(scale, (list, tuple)) else list(scale)
+        self.to_k_ip = nn.ModuleList([nn.Linear(cross_attention_dim, hidden_size, bias=False)])
+        self.to_v_ip = nn.ModuleList([nn.Linear(cross_attention_dim, hidden_size, bias=False)])
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
+        check_unet_preconditions(attn, hidden_states, attention_mask)
+        x = hidden_states
+        text, ip = split_ip_states(encoder_hidden_states, self.num_tokens, x.shape[0])
+        q = _cabi.linear(x, attn.to_q.weight)
+        hid = _cabi.attn_core(q, _cabi.linear(text, attn.to_k.weight), _cabi.linear(text, attn.to_v.weight), None,
+                              attn.heads, _cabi.PAID_PLAIN, False, attn.scale)
+        _cabi.attn_core(q, _cabi.linear(ip, self.to_k_ip[0].weight), _cabi.linear(ip, self.to_v_ip[0].weight), None,
+                        attn.heads, _cabi.PAID_PLAIN, False, attn.scale, out=hid, accumulate=True,
+                        out_scale=float(self.scale[0]))
+        return _cabi.linear(hid, attn.to_out[0].weight, attn.to_out[0].bias)
+
+
 def check_unet_preconditions(attn, hidden_states, attention_mask):
     """The kernels implement the UNet transformer-block case of the processors; the
     branches that are dead there (interpolation.py:586-611, 618-621, 669-677) are

@@ -48,6 +48,9 @@ struct TcArgs {
   float scale_log2;
   const float* coef;
   void* out;
+  int accumulate;
+  float out_scale;
+  const float* out_frame_scale;
   int per_frame[3];  // slot K/V map has one matrix per frame (1) or a single shared matrix (0)
 };
 
@@ -324,7 +327,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // per step, and a parity wait cannot be used on a barrier whose phases this thread has skipped).
     ptx::mbar_wait(&bar->acc_final[t], 0);
     ptx::tc_fence_after();
-    const float cf[2] = {seg.a_active ? plan.wA / l_st[0] : 0.f, seg.b_active ? plan.wB / l_st[1] : 0.f};
+    const float os = a.out_scale * (a.out_frame_scale ? a.out_frame_scale[n] : 1.f);
+    const float cf[2] = {seg.a_active ? os * plan.wA / l_st[0] : 0.f, seg.b_active ? os * plan.wB / l_st[1] : 0.f};
     const bool active[2] = {seg.a_active, seg.b_active};
     const int row = row0 + t * BM + quad * 32 + lane;
     T* dst = (T*)a.out + ((long long)n * a.S + row) * (a.heads * D) + head * D;
@@ -343,6 +347,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int e = 0; e < 32; ++e) acc[e] = fmaf(cf[st], __uint_as_float(o[e]), acc[e]);
       }
       if (row < a.S) {
+        if (a.accumulate) {  // out += ...: the IP-Adapter second attention (CTA-uniform branch)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint4 old = *reinterpret_cast<const uint4*>(dst + h * 32 + v * 8);
+            const T* o8 = reinterpret_cast<const T*>(&old);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[v * 8 + e] += to_f32(o8[e]);
+          }
+        }
 #pragma unroll
         for (int v = 0; v < 4; ++v)
           *reinterpret_cast<uint4*>(dst + h * 32 + v * 8) =
@@ -383,10 +396,11 @@ int launch_attn_tc(const CoreArgs& a, cudaStream_t stream) {
   const long long C = (long long)a.heads * D;
   int st = make_tmap_heads(&maps[0], a.q, a.dtype, a.N, a.S, a.heads, D, (long long)a.S * C, BM);
   if (st != PAID_OK) return st;
-  if ((st = make_tmap_heads(&maps[1], a.k, a.dtype, a.N, a.L, a.heads, D, (long long)a.L * C, BN)) != PAID_OK) return st;
-  if ((st = make_tmap_heads(&maps[2], a.v, a.dtype, a.N, a.L, a.heads, D, (long long)a.L * C, BN)) != PAID_OK) return st;
+  const long long kv_frames = a.stride0 ? a.N : 1;
+  if ((st = make_tmap_heads(&maps[1], a.k, a.dtype, kv_frames, a.L, a.heads, D, a.stride0, BN)) != PAID_OK) return st;
+  if ((st = make_tmap_heads(&maps[2], a.v, a.dtype, kv_frames, a.L, a.heads, D, a.stride0, BN)) != PAID_OK) return st;
   TcArgs ta{};
-  ta.per_frame[0] = 1;
+  ta.per_frame[0] = a.stride0 ? 1 : 0;
   const void* kk[2] = {a.k1, a.k2};
   const void* vv[2] = {a.v1, a.v2};
   const long long strides[2] = {a.stride1, a.stride2};
@@ -406,6 +420,7 @@ int launch_attn_tc(const CoreArgs& a, cudaStream_t stream) {
   ta.begin_frame = a.begin_frame; ta.end_frame = a.end_frame;
   ta.scale_log2 = a.scale * kLog2e;
   ta.coef = a.coef; ta.out = a.out;
+  ta.accumulate = a.accumulate; ta.out_scale = a.out_scale; ta.out_frame_scale = a.out_frame_scale;
   return a.dtype == PAID_F16 ? launch_t<__half>(maps, ta, stream) : launch_t<__nv_bfloat16>(maps, ta, stream);
 }
 

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kWarps * 32) attn_generic_kernel(CoreArgs a) {
     const bool use = s == 0 ? plan.use0 : (s == 1 ? plan.use1 : plan.use2);
     if (!use) continue;  // block-uniform
     const T* kbase; const T* vbase;
-    if (s == 0) { kbase = (const T*)a.k + (long long)n * a.L * C; vbase = (const T*)a.v + (long long)n * a.L * C; }
+    if (s == 0) { kbase = (const T*)a.k + n * a.stride0; vbase = (const T*)a.v + n * a.stride0; }
     else if (s == 1) { kbase = (const T*)a.k1 + n * a.stride1; vbase = (const T*)a.v1 + n * a.stride1; }
     else { kbase = (const T*)a.k2 + n * a.stride2; vbase = (const T*)a.v2 + n * a.stride2; }
     kbase += head * d; vbase += head * d;
@@ -218,10 +218,15 @@ __global__ void __launch_bounds__(kWarps * 32) attn_generic_kernel(CoreArgs a) {
     if (row >= a.S) continue;
     float cf0, cf1, cf2;
     merge_coefficients(plan, mS[0][r], lS[0][r], mS[1][r], lS[1][r], mS[2][r], lS[2][r], cf0, cf1, cf2);
+    const float os = a.out_scale * (a.out_frame_scale ? a.out_frame_scale[n] : 1.f);
 #pragma unroll
     for (int jj = 0; jj < DPL; ++jj) {
       int j = lane + 32 * jj;
-      if (j < d) out[(long long)row * C + j] = from_f32<T>(cf0 * O[0][r][jj] + cf1 * O[1][r][jj] + cf2 * O[2][r][jj]);
+      if (j < d) {
+        float r0 = os * (cf0 * O[0][r][jj] + cf1 * O[1][r][jj] + cf2 * O[2][r][jj]);
+        if (a.accumulate) r0 += to_f32(out[(long long)row * C + j]);
+        out[(long long)row * C + j] = from_f32<T>(r0);
+      }
     }
   }
 }

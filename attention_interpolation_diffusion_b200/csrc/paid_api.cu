@@ -232,6 +232,11 @@ int paid_attn_core(const PaidCoreParams* p, void* cuda_stream) {
   a.N = p->N; a.S = p->S; a.L = p->L; a.heads = p->heads; a.head_dim = p->head_dim;
   a.scale = p->scale; a.begin_frame = p->begin_frame; a.end_frame = p->end_frame;
   a.q = p->q; a.k = p->k; a.v = p->v; a.coef = p->coef; a.out = p->out;
+  a.accumulate = p->accumulate ? 1 : 0;
+  a.out_scale = p->out_scale == 0.f ? 1.f : p->out_scale;
+  a.out_frame_scale = p->out_frame_scale;
+  if (p->kv_broadcast && p->mode != PAID_PLAIN) return fail(PAID_EINVAL, "kv_broadcast is only valid in PLAIN mode");
+  a.stride0 = p->kv_broadcast ? 0 : (long long)p->L * p->heads * p->head_dim;
   void* kx = nullptr; void* vx = nullptr;
   if (p->mode == PAID_INNER) {
     uint64_t need = paid_attn_core_workspace_bytes(p);
@@ -284,6 +289,7 @@ int paid_attn_forward(const PaidAttnParams* p, void* cuda_stream) {
   a.N = p->N; a.S = p->S; a.L = p->L; a.heads = p->heads; a.head_dim = p->C / p->heads;
   a.scale = p->scale; a.begin_frame = p->begin_frame; a.end_frame = p->end_frame;
   a.q = Q; a.k = K; a.v = V; a.coef = p->coef; a.out = H;
+  a.accumulate = 0; a.out_scale = 1.f; a.out_frame_scale = nullptr; a.stride0 = (long long)p->L * p->C;
   void* kx = p->mode == PAID_INNER ? base + ws.kx : nullptr;
   void* vx = p->mode == PAID_INNER ? base + ws.vx : nullptr;
   if ((st = resolve_slots(a, p->mode == PAID_PLAIN ? nullptr : p->kv_ext, kx, vx, stream)) != PAID_OK) return st;

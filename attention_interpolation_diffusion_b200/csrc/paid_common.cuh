@@ -128,6 +128,11 @@ struct CoreArgs {
   const void* k2; const void* v2; long long stride2;
   const float* coef;
   void* out;
+  // out = (accumulate ? out : 0) + out_scale * (out_frame_scale ? out_frame_scale[n] : 1) * attention
+  int accumulate;
+  float out_scale;
+  const float* out_frame_scale;
+  long long stride0;  // frame stride of k / v in elements (0: one matrix shared by all frames)
 };
 
 // kernel launchers (each returns a PaidStatus)

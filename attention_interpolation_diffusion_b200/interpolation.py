@@ -29,7 +29,7 @@ import torch
 from torch import nn
 
 from . import _cabi
-from .attention import PaidAttnProcessor, check_unet_preconditions
+from .attention import PaidAttnProcessor, check_unet_preconditions, split_ip_states
 from .prior import generate_beta_tensor
 
 _coef_cache: dict = {}
@@ -145,3 +145,97 @@ class InnerInterpolatedAttnProcessor(InterpolatedAttnProcessor):
                  beta: float = 1, original_attn=None):
         super().__init__(t=t, size=size, is_fused=is_fused, alpha=alpha, beta=beta)
         self.original_attn = original_attn
+
+
+# ------------------------------------------------------------------------------------------------------
+# IP-Adapter variants (reference interpolation.py:51-545; installed by load_aid_ip_adapter, sdxl:1089-1126).
+# The text part is the processor call above; the image-token part is a second attention of the SAME queries,
+# accumulated into the text result by the attention kernel itself (PaidCoreParams.accumulate / out_scale).
+# The reference hard-codes a batch of 3 (expand(3, ...), [::3], [6:9]); here any number of frames works and
+# the image tokens are passed per frame as (N, T, Cc) (the reference's 3x-repeated rows are accepted too).
+# ------------------------------------------------------------------------------------------------------
+class _InterpolatedIPAttnProcessor(InterpolatedAttnProcessor):
+    text_mode = _cabi.PAID_OUTER
+
+    def __init__(self, t: Optional[float] = None, size: int = 7, is_fused: bool = False, alpha: float = 1,
+                 beta: float = 1, ip_attn=None):
+        super().__init__(t=t, size=size, is_fused=is_fused, alpha=alpha, beta=beta)
+        self.num_tokens = ip_attn.num_tokens if hasattr(ip_attn, "num_tokens") else (16,)
+        self.scale = ip_attn.scale if hasattr(ip_attn, "scale") else None
+        self.ip_attn = ip_attn
+
+    def _parts(self, attn, hidden_states, encoder_hidden_states, attention_mask):
+        check_unet_preconditions(attn, hidden_states, attention_mask)
+        x = hidden_states
+        if self.shard is not None:
+            raise NotImplementedError("frame sharding of the IP-Adapter variants is not implemented")
+        if x.shape[0] != self.size or self.coef.numel() != self.size:
+            raise ValueError(f"batch size {x.shape[0]} / {self.coef.numel()} coefficients != processor size {self.size}")
+        text, ip = (None, None) if encoder_hidden_states is None else split_ip_states(
+            encoder_hidden_states, self.num_tokens, x.shape[0])
+        coef = _device_coef(self.coef, x.device)
+        src = x if text is None else text
+        q = _cabi.linear(x, attn.to_q.weight, flags=self.kernel_flags)
+        k = _cabi.linear(src, attn.to_k.weight, flags=self.kernel_flags)
+        v = _cabi.linear(src, attn.to_v.weight, flags=self.kernel_flags)
+        return x, ip, coef, q, k, v
+
+    def _ip_kv(self, ip):
+        return (_cabi.linear(ip, self.ip_attn.to_k_ip[0].weight, flags=self.kernel_flags),
+                _cabi.linear(ip, self.ip_attn.to_v_ip[0].weight, flags=self.kernel_flags))
+
+    def _out(self, attn, hid):
+        return _cabi.linear(hid, attn.to_out[0].weight, attn.to_out[0].bias, flags=self.kernel_flags)
+
+
+class OuterInterpolatedIPAttnProcessor(_InterpolatedIPAttnProcessor):
+    r"""Outer interpolation of the text attention plus ``scale[0]`` times the outer interpolation of the image-token
+    attention (reference interpolation.py:214-387)."""
+    mode = _cabi.PAID_OUTER
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
+        if not self.activated:
+            return self.ip_attn(attn, hidden_states, encoder_hidden_states, attention_mask, temb)
+        x, ip, coef, q, k, v = self._parts(attn, hidden_states, encoder_hidden_states, attention_mask)
+        hid = _cabi.attn_core(q, k, v, coef, attn.heads, _cabi.PAID_OUTER, self.is_fused, attn.scale, flags=self.kernel_flags)
+        if ip is not None:
+            kip, vip = self._ip_kv(ip)
+            _cabi.attn_core(q, kip, vip, coef, attn.heads, _cabi.PAID_OUTER, self.is_fused, attn.scale, flags=self.kernel_flags,
+                            out=hid, accumulate=True, out_scale=float(self.scale[0]))
+        return self._out(attn, hid)
+
+
+class InnerInterpolatedIPAttnProcessor(_InterpolatedIPAttnProcessor):
+    r"""Inner interpolation of the text attention plus ``scale[0]`` times the attention over each frame's OWN image
+    tokens -- the reference computes lerped image K/V but then attends with ``key`` / ``value`` of the frame itself
+    (interpolation.py:512-527); that behaviour is kept (reference interpolation.py:390-545)."""
+    mode = _cabi.PAID_INNER
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
+        if not self.activated:
+            return self.ip_attn(attn, hidden_states, encoder_hidden_states, attention_mask, temb)
+        x, ip, coef, q, k, v = self._parts(attn, hidden_states, encoder_hidden_states, attention_mask)
+        hid = _cabi.attn_core(q, k, v, coef, attn.heads, _cabi.PAID_INNER, self.is_fused, attn.scale, flags=self.kernel_flags)
+        if ip is not None:
+            kip, vip = self._ip_kv(ip)
+            _cabi.attn_core(q, kip, vip, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale, flags=self.kernel_flags,
+                            out=hid, accumulate=True, out_scale=float(self.scale[0]))
+        return self._out(attn, hid)
+
+
+class ScaleControlIPAttnProcessor(_InterpolatedIPAttnProcessor):
+    r"""Image-prompt strength control: text attention (outer-interpolated while activated, plain otherwise) plus
+    ``coef[n]`` times the attention over the END frame's image tokens (reference interpolation.py:51-211)."""
+    mode = _cabi.PAID_OUTER
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
+        x, ip, coef, q, k, v = self._parts(attn, hidden_states, encoder_hidden_states, attention_mask)
+        if self.activated:
+            hid = _cabi.attn_core(q, k, v, coef, attn.heads, _cabi.PAID_OUTER, self.is_fused, attn.scale, flags=self.kernel_flags)
+        else:
+            hid = _cabi.attn_core(q, k, v, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale, flags=self.kernel_flags)
+        if ip is not None:
+            kip, vip = self._ip_kv(ip[-1:].contiguous())          # the end image for every frame (ip[0][6:9])
+            _cabi.attn_core(q, kip, vip, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale, flags=self.kernel_flags,
+                            out=hid, accumulate=True, out_frame_scale=coef, kv_broadcast=True)
+        return self._out(attn, hid)

@@ -21,7 +21,10 @@ from typing import Optional
 
 import torch
 
-from .interpolation import InnerInterpolatedAttnProcessor, OuterInterpolatedAttnProcessor
+from .attention import PaidIPAdapterAttnProcessor
+from .interpolation import (InnerInterpolatedAttnProcessor, InnerInterpolatedIPAttnProcessor,
+                            OuterInterpolatedAttnProcessor, OuterInterpolatedIPAttnProcessor,
+                            ScaleControlIPAttnProcessor)
 from .prior import generate_beta_tensor
 from .sharding import FrameShard
 from .unet_harness import UNetHarness
@@ -127,6 +130,27 @@ class InterpolationPipeline:
                 attn_procs[name] = old
         self.unet.set_attn_processor(attn_procs)
         self._graphs.clear()               # captured forwards bake the processor objects in
+
+    def load_aid_ip_adapter(self, num_tokens: int = 16, scale: float = 1.0, t: Optional[float] = 0.5,
+                            is_fused: bool = True, early: str = "fused_outer", size: int = 7, alpha: float = 1,
+                            beta: float = 1):
+        """Mirror of load_aid_ip_adapter (sdxl:1089-1126).  The reference first calls diffusers' load_ip_adapter, which
+        gives every cross-attention layer an IPAdapterAttnProcessor2_0 with to_k_ip / to_v_ip; without checkpoints
+        those are random-init ``PaidIPAdapterAttnProcessor`` objects here.  Then every processor is wrapped."""
+        cls = {"fused_outer": OuterInterpolatedIPAttnProcessor, "fused_inner": InnerInterpolatedIPAttnProcessor,
+               "scale_control": ScaleControlIPAttnProcessor}[early]
+        mods = self.unet._attention_modules()
+        attn_procs = {}
+        for name, m in mods.items():
+            old = m.processor
+            if name.endswith("attn2.processor"):
+                old = PaidIPAdapterAttnProcessor(m.to_q.in_features, m.to_k.in_features, (num_tokens,), scale)
+                old = old.to(device=m.to_q.weight.device, dtype=m.to_q.weight.dtype)
+            elif isinstance(old, (OuterInterpolatedAttnProcessor, InnerInterpolatedAttnProcessor)):
+                old = old.original_attn
+            attn_procs[name] = cls(t=t, size=size, is_fused=is_fused, alpha=alpha, beta=beta, ip_attn=old)
+        self.unet.set_attn_processor(attn_procs)
+        self._graphs.clear()
 
     def activate_aid(self, it: float):
         for name, proc in self.unet.attn_processors.items():

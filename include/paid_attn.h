@@ -109,6 +109,12 @@ typedef struct PaidCoreParams {
   void* out;            /* (N,S,heads*head_dim) attention output before to_out */
   void* workspace;      /* INNER only: 2*N*L*heads*head_dim elements for the lerped K/V; else may be NULL */
   uint64_t workspace_bytes;
+  /* output combination (IP-Adapter variants, interpolation.py:364-367, 530, 196):
+   *   out = (accumulate ? out : 0) + out_scale * (out_frame_scale ? out_frame_scale[n] : 1) * attention */
+  int32_t accumulate;
+  float out_scale;              /* 0 is read as 1 (zero-initialised structs keep the plain behaviour) */
+  const float* out_frame_scale; /* NULL or (N,) fp32 */
+  int32_t kv_broadcast;         /* 1: k and v are one (L, C) matrix shared by all frames (PLAIN mode only) */
 } PaidCoreParams;
 
 int paid_attn_abi_version(void);

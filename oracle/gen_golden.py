@@ -160,6 +160,54 @@ def main():
     print("worst oracle-vs-reference abs diff:", worst)
 
 
+class RefIPAttn(nn.Module):
+    """Fields of diffusers IPAdapterAttnProcessor2_0 read by the IP variants (interpolation.py:70-74, 137-138)."""
+
+    def __init__(self, wk_ip, wv_ip, T, scale):
+        super().__init__()
+        C, Cc = wk_ip.shape
+        self.num_tokens, self.scale = (T,), [scale]
+        self.to_k_ip = nn.ModuleList([nn.Linear(Cc, C, bias=False)])
+        self.to_v_ip = nn.ModuleList([nn.Linear(Cc, C, bias=False)])
+        with torch.no_grad():
+            self.to_k_ip[0].weight.copy_(wk_ip), self.to_v_ip[0].weight.copy_(wv_ip)
+
+
+# name, C, Cc, heads, S, L, T(image tokens)   -- the reference IP processors are hard-coded to a batch of 3
+IP_CASES = [("ip_d64", 128, 96, 2, 40, 13, 4), ("ip_d40_t16", 80, 48, 2, 24, 77, 16)]
+
+
+def main_ip():
+    ref = sys.modules["interpolation"]
+    N, ip_scale = 3, 0.7
+    for seed, (name, C, Cc, h, S, L, T) in enumerate(IP_CASES):
+        w = O.make_layer(C, Cc, h, seed=300 + seed)
+        x, ctx = O.make_inputs(N, S, C, L, Cc, seed=300 + seed)
+        ip, wk_ip, wv_ip = O.make_ip(N, T, C, Cc, seed=300 + seed)
+        coef = O.coefficients(N, t=0.35)
+        ip9 = ip.repeat_interleave(3, dim=0)        # the reference's row layout [s,s,s,t,t,t,e,e,e] (sdxl:2146-2185)
+        blob = dict(meta=np.array([C, Cc, h, S, L, N, T], dtype=np.int64), coef=coef.numpy(), ip_scale=np.float32(ip_scale),
+                    x=x.numpy(), ctx=ctx.numpy(), ip=ip.numpy(), wk_ip=wk_ip.numpy(), wv_ip=wv_ip.numpy(),
+                    wq=w.wq.numpy(), wk=w.wk.numpy(), wv=w.wv.numpy(), wo=w.wo.numpy(), bo=w.bo.numpy())
+        runs = {
+            "outer_fused": (ref.OuterInterpolatedIPAttnProcessor, True, lambda: O.forward_ip_outer(x, ctx, ip, w, wk_ip, wv_ip, coef, True, ip_scale)),
+            "outer_pure": (ref.OuterInterpolatedIPAttnProcessor, False, lambda: O.forward_ip_outer(x, ctx, ip, w, wk_ip, wv_ip, coef, False, ip_scale)),
+            "inner_fused": (ref.InnerInterpolatedIPAttnProcessor, True, lambda: O.forward_ip_inner(x, ctx, ip, w, wk_ip, wv_ip, coef, True, ip_scale)),
+            "scale_fused": (ref.ScaleControlIPAttnProcessor, True, lambda: O.forward_ip_scale_control(x, ctx, ip, w, wk_ip, wv_ip, coef, True, True)),
+            "scale_pure": (ref.ScaleControlIPAttnProcessor, False, lambda: O.forward_ip_scale_control(x, ctx, ip, w, wk_ip, wv_ip, coef, False, True)),
+        }
+        for key, (cls, fused, orc) in runs.items():
+            proc = cls(t=0.35, is_fused=fused, ip_attn=RefIPAttn(wk_ip, wv_ip, T, ip_scale))
+            with torch.no_grad():
+                y = proc(RefAttention(w), x, encoder_hidden_states=(ctx, [ip9]))
+            err = (y - orc()).abs().max().item()
+            assert err < 5e-6, (name, key, err)
+            blob["y_" + key] = y.numpy()
+            print(f"{name:12s} {key:12s} oracle-vs-reference {err:.2e}")
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **blob)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     main()
+    main_ip()

@@ -286,3 +286,67 @@ def error_metrics(test: torch.Tensor, ref: torch.Tensor):
 def within_tolerance(test, ref, rel_rms=REL_RMS_TOL, max_abs=MAX_ABS_TOL_X_RMS):
     m = error_metrics(test, ref)
     return (m["rel_rms"] <= rel_rms and m["max_abs_over_rms"] <= max_abs), m
+
+
+# ----------------------------------------------------------------------------
+# IP-Adapter variants (interpolation.py:51-545).  ip: (N, T, Cc) image tokens of each frame (the reference
+# feeds a 3x row-repeated tensor for its hard-coded batch of 3 and un-repeats it with [::3] / [6:9]).
+# ----------------------------------------------------------------------------
+def _ip_parts(x, ctx, ip, w, wk_ip, wv_ip):
+    q, k, v = _project(x, ctx, w)
+    return q, k, v, ip @ wk_ip.T, ip @ wv_ip.T
+
+
+def forward_ip_outer(x, ctx, ip, w: LayerWeights, wk_ip, wv_ip, coef, fused: bool, ip_scale: float) -> torch.Tensor:
+    """OuterInterpolatedIPAttnProcessor (interpolation.py:240-387): outer interpolation of the text attention plus
+    ip_scale times the outer interpolation of the image-token attention, same queries."""
+    h, scale = w.heads, (x.shape[-1] // w.heads) ** -0.5
+    q, k, v, kip, vip = _ip_parts(x, ctx, ip, w, wk_ip, wv_ip)
+    hid = _direct_core(q, k, v, (k[0], v[0], k[-1], v[-1]), coef, MODE_OUTER, fused, scale, h)
+    hid = hid + ip_scale * _direct_core(q, kip, vip, (kip[0], vip[0], kip[-1], vip[-1]), coef, MODE_OUTER, fused, scale, h)
+    return hid @ w.wo.T + w.bo
+
+
+def forward_ip_inner(x, ctx, ip, w: LayerWeights, wk_ip, wv_ip, coef, fused: bool, ip_scale: float) -> torch.Tensor:
+    """InnerInterpolatedIPAttnProcessor (interpolation.py:417-545).  Reference quirk kept: the image part attends
+    with each frame's OWN image K/V only (:525-527; the lerped key_cross of :512-523 is computed but unused)."""
+    h, scale = w.heads, (x.shape[-1] // w.heads) ** -0.5
+    q, k, v, kip, vip = _ip_parts(x, ctx, ip, w, wk_ip, wv_ip)
+    hid = _direct_core(q, k, v, (k[0], v[0], k[-1], v[-1]), coef, MODE_INNER, fused, scale, h)
+    hid = hid + ip_scale * _direct_core(q, kip, vip, None, None, MODE_PLAIN, False, scale, h)
+    return hid @ w.wo.T + w.bo
+
+
+def forward_ip_scale_control(x, ctx, ip, w: LayerWeights, wk_ip, wv_ip, coef, fused: bool, activated: bool) -> torch.Tensor:
+    """ScaleControlIPAttnProcessor (interpolation.py:76-211): text attention (outer-interpolated when activated,
+    plain otherwise) plus coef[n] times the attention over the END frame's image tokens (ip[0][6:9], :187-196)."""
+    h, scale = w.heads, (x.shape[-1] // w.heads) ** -0.5
+    N = x.shape[0]
+    q, k, v, kip, vip = _ip_parts(x, ctx, ip, w, wk_ip, wv_ip)
+    if activated:
+        hid = _direct_core(q, k, v, (k[0], v[0], k[-1], v[-1]), coef, MODE_OUTER, fused, scale, h)
+    else:
+        hid = _direct_core(q, k, v, None, None, MODE_PLAIN, False, scale, h)
+    ke, ve = kip[-1:].expand(N, -1, -1), vip[-1:].expand(N, -1, -1)
+    hid = hid + coef.to(x.dtype).reshape(N, 1, 1) * _direct_core(q, ke, ve, None, None, MODE_PLAIN, False, scale, h)
+    return hid @ w.wo.T + w.bo
+
+
+def forward_ip_stock(x, ctx, ip, w: LayerWeights, wk_ip, wv_ip, ip_scale: float) -> torch.Tensor:
+    """Stock IP-Adapter attention (diffusers IPAdapterAttnProcessor2_0, the deactivated branch :248-251):
+    plain text attention + ip_scale * plain image-token attention."""
+    h, scale = w.heads, (x.shape[-1] // w.heads) ** -0.5
+    q, k, v, kip, vip = _ip_parts(x, ctx, ip, w, wk_ip, wv_ip)
+    hid = _direct_core(q, k, v, None, None, MODE_PLAIN, False, scale, h)
+    hid = hid + ip_scale * _direct_core(q, kip, vip, None, None, MODE_PLAIN, False, scale, h)
+    return hid @ w.wo.T + w.bo
+
+
+def make_ip(N: int, T: int, C: int, Cc: int, seed: int, dtype=torch.float32):
+    """Seeded image tokens (N,T,Cc) and to_k_ip / to_v_ip weights (C,Cc)."""
+    rs = np.random.RandomState(seed + 104729)
+    b = 1.0 / math.sqrt(Cc)
+    ip = torch.from_numpy(rs.standard_normal((N, T, Cc))).to(dtype)
+    wk = torch.from_numpy(rs.uniform(-b, b, size=(C, Cc))).to(dtype)
+    wv = torch.from_numpy(rs.uniform(-b, b, size=(C, Cc))).to(dtype)
+    return ip, wk, wv

@@ -12,7 +12,36 @@ MODES = [("outer", False), ("outer", True), ("inner", False), ("inner", True)]
 
 
 def case_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+                  if not n.startswith("ip_"))
+
+
+def ip_case_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "ip_*.npz")))
+
+
+IP_RUNS = ["outer_fused", "outer_pure", "inner_fused", "scale_fused", "scale_pure"]
+
+
+def load_ip_case(name):
+    """IP-Adapter vectors written by the reference's IP processors (batch of 3)."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    C, Cc, h, S, L, N, T = (int(v) for v in z["meta"])
+    t = lambda k: torch.from_numpy(z[k])
+    w = O.LayerWeights(t("wq"), t("wk"), t("wv"), t("wo"), t("bo"), heads=h)
+    return dict(name=name, w=w, x=t("x"), ctx=t("ctx"), ip=t("ip"), wk_ip=t("wk_ip"), wv_ip=t("wv_ip"), coef=t("coef"),
+                ip_scale=float(z["ip_scale"]), outs={k: t("y_" + k) for k in IP_RUNS}, h=h, T=T, N=N)
+
+
+def oracle_ip(c, run, x=None, ctx=None, ip=None, w=None, wk_ip=None, wv_ip=None):
+    x, ctx, ip = (c["x"] if x is None else x), (c["ctx"] if ctx is None else ctx), (c["ip"] if ip is None else ip)
+    w, wk_ip, wv_ip = (c["w"] if w is None else w), (c["wk_ip"] if wk_ip is None else wk_ip), (c["wv_ip"] if wv_ip is None else wv_ip)
+    kind, fused = run.split("_")[0], run.endswith("fused")
+    if kind == "outer":
+        return O.forward_ip_outer(x, ctx, ip, w, wk_ip, wv_ip, c["coef"], fused, c["ip_scale"])
+    if kind == "inner":
+        return O.forward_ip_inner(x, ctx, ip, w, wk_ip, wv_ip, c["coef"], fused, c["ip_scale"])
+    return O.forward_ip_scale_control(x, ctx, ip, w, wk_ip, wv_ip, c["coef"], fused, True)
 
 
 def load_case(name):

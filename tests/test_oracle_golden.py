@@ -4,7 +4,7 @@ import pytest
 import torch
 
 import paid_oracle as O
-from golden_util import MODES, case_names, load_case
+from golden_util import IP_RUNS, MODES, case_names, ip_case_names, load_case, load_ip_case, oracle_ip
 
 
 @pytest.mark.parametrize("name", case_names())
@@ -17,6 +17,13 @@ def test_oracle_matches_reference_vectors(name):
             assert (y - y_ref).abs().max().item() < 2e-6, (name, m, fused, fn.__name__)
         y = O.forward_chunked(c["x"], c["ctx"], c["w"], c["coef"], mode, fused, rows=17)[:, ::c["stride"]]
         assert (y - y_ref).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("name", ip_case_names())
+def test_ip_oracle_matches_reference_vectors(name):
+    c = load_ip_case(name)
+    for run in IP_RUNS:
+        assert (oracle_ip(c, run) - c["outs"][run]).abs().max().item() < 2e-6, (name, run)
 
 
 def test_golden_set_is_complete():

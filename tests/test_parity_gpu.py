@@ -269,3 +269,70 @@ def test_pipeline_cuda_graph_replay_equals_eager(cabi):
     assert pipe.graph_kernel_launches > 0 and len(pipe._graphs) == 2
     assert torch.equal(first, again)
     check(first.float().cpu(), eager.float().cpu(), "graph replay vs eager", rel=1e-3)
+
+
+def _ip_setup(c, dtype=torch.float16):
+    from attention_interpolation_diffusion_b200 import Attention, PaidIPAdapterAttnProcessor
+    w = c["w"]
+    C, Cc = w.wq.shape[0], w.wk.shape[1]
+    attn = Attention(C, Cc, c["h"], C // c["h"])
+    ipa = PaidIPAdapterAttnProcessor(C, Cc, num_tokens=(c["T"],), scale=c["ip_scale"])
+    with torch.no_grad():
+        attn.to_q.weight.copy_(w.wq), attn.to_k.weight.copy_(w.wk), attn.to_v.weight.copy_(w.wv)
+        attn.to_out[0].weight.copy_(w.wo), attn.to_out[0].bias.copy_(w.bo)
+        ipa.to_k_ip[0].weight.copy_(c["wk_ip"]), ipa.to_v_ip[0].weight.copy_(c["wv_ip"])
+    return attn.cuda().to(dtype), ipa.cuda().to(dtype)
+
+
+def test_ip_adapter_variants_against_reference_vectors(cabi):
+    """the three IP-Adapter processors against the vectors written by the reference's own IP
+    processors (batch of 3, image tokens in the reference's 3x-repeated row layout), plus the deactivated branch."""
+    from golden_util import IP_RUNS, ip_case_names, load_ip_case, oracle_ip
+    from attention_interpolation_diffusion_b200 import (InnerInterpolatedIPAttnProcessor, OuterInterpolatedIPAttnProcessor,
+                                                        ScaleControlIPAttnProcessor)
+    classes = {"outer": OuterInterpolatedIPAttnProcessor, "inner": InnerInterpolatedIPAttnProcessor,
+               "scale": ScaleControlIPAttnProcessor}
+    for name in ip_case_names():
+        c = load_ip_case(name)
+        attn, ipa = _ip_setup(c)
+        ip9 = c["ip"].repeat_interleave(3, dim=0)
+        r = rounded
+        wr = O.LayerWeights(*(r(t) for t in (c["w"].wq, c["w"].wk, c["w"].wv, c["w"].wo, c["w"].bo)), heads=c["h"])
+        for run in IP_RUNS:
+            proc = classes[run.split("_")[0]](t=float(c["coef"][1]), is_fused=run.endswith("fused"), ip_attn=ipa)
+            attn.set_processor(proc)
+            for flags in (0, cabi.FLAG_GENERIC_KERNELS):
+                proc.kernel_flags = flags
+                y = attn(dev(c["x"]), encoder_hidden_states=(dev(c["ctx"]), [dev(ip9)])).float().cpu()
+                check(y, c["outs"][run], (name, run, flags, "vs reference golden"))
+                check(y, oracle_ip(c, run, r(c["x"]), r(c["ctx"]), r(c["ip"]), wr, r(c["wk_ip"]), r(c["wv_ip"])),
+                      (name, run, flags, "vs oracle on rounded inputs"), rel=1e-3)
+        # deactivated outer / inner -> stock IP attention; appended-token form of encoder_hidden_states
+        proc = OuterInterpolatedIPAttnProcessor(t=0.5, is_fused=True, ip_attn=ipa)
+        proc.deactivate()
+        attn.set_processor(proc)
+        y = attn(dev(c["x"]), encoder_hidden_states=torch.cat([dev(c["ctx"]), dev(c["ip"])], dim=1)).float().cpu()
+        ref = O.forward_ip_stock(r(c["x"]), r(c["ctx"]), r(c["ip"]), wr, r(c["wk_ip"]), r(c["wv_ip"]), c["ip_scale"])
+        check(y, ref, (name, "deactivated stock IP"), rel=1e-3)
+
+
+def test_ip_adapter_variants_n_frames(cabi):
+    """Generalisation the reference lacks: N = 6 frames, per-frame image tokens (N, T, Cc), d = 64 (tcgen05 path)."""
+    from attention_interpolation_diffusion_b200 import (Attention, OuterInterpolatedIPAttnProcessor,
+                                                        PaidIPAdapterAttnProcessor, ScaleControlIPAttnProcessor)
+    N, S, C, h, Cc, L, T = 6, 300, 128, 2, 96, 77, 16
+    w = O.make_layer(C, Cc, h, 77)
+    x, ctx = O.make_inputs(N, S, C, L, Cc, 77)
+    ip, wk_ip, wv_ip = O.make_ip(N, T, C, Cc, 77)
+    c = dict(w=w, h=h, T=T, ip_scale=0.6, wk_ip=wk_ip, wv_ip=wv_ip)
+    attn, ipa = _ip_setup(c)
+    coef = O.coefficients(N, 3, 3)
+    r = rounded
+    wr = O.LayerWeights(*(r(t) for t in (w.wq, w.wk, w.wv, w.wo, w.bo)), heads=h)
+    for cls, fn in ((OuterInterpolatedIPAttnProcessor, lambda: O.forward_ip_outer(r(x), r(ctx), r(ip), wr, r(wk_ip), r(wv_ip), coef, True, 0.6)),
+                    (ScaleControlIPAttnProcessor, lambda: O.forward_ip_scale_control(r(x), r(ctx), r(ip), wr, r(wk_ip), r(wv_ip), coef, True, True))):
+        proc = cls(size=N, is_fused=True, alpha=3, beta=3, ip_attn=ipa)
+        attn.set_processor(proc)
+        y = attn(dev(x), encoder_hidden_states=(dev(ctx), [dev(ip)])).float().cpu()
+        assert cabi.last_kernel() == "tcgen05"
+        check(y, fn(), (cls.__name__, "N=6"), rel=1e-3)
