@@ -7,7 +7,8 @@
 //
 // CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2-5 epilogue.
 // One 128x128 output tile per CTA; 3-stage 32 KB ring so two CTAs share an SM and one CTA's epilogue
-// overlaps the other's main loop.
+// overlaps the other's main loop.  Up to three weight matrices that share the same input (q/k/v of a
+// self-attention layer, k/v of a cross-attention layer) run as ONE launch: blockIdx.z picks the group.
 #include <type_traits>
 
 #include "paid_common.cuh"
@@ -21,10 +22,20 @@ constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTE
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr int TMEM_COLS = 128;
 
+struct GroupPtrs {
+  const void* bias[3];
+  void* y[3];
+};
+
 template <typename T>
 __global__ void __launch_bounds__(192, 2)
-linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const T* __restrict__ bias, T* __restrict__ y, long long M, int N, int K) {
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                 const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
+                 const GroupPtrs gp, long long M, int N, int K) {
+  const int group = blockIdx.z;
+  const CUtensorMap& tmB = group == 0 ? tmB0 : (group == 1 ? tmB1 : tmB2);
+  const T* __restrict__ bias = (const T*)gp.bias[group];
+  T* __restrict__ y = (T*)gp.y[group];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -115,7 +126,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <typename T>
-int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const void* bias, void* y, long long M, int N, int K,
+int launch_t(const CUtensorMap& tmA, const CUtensorMap* tmB, const GroupPtrs& gp, int groups, long long M, int N, int K,
              cudaStream_t stream) {
   auto kern = linear_tc_kernel<T>;
   static bool configured = false;
@@ -123,8 +134,8 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const void* bias, v
     PAID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  dim3 grid((N + BN - 1) / BN, (unsigned)((M + BM - 1) / BM));
-  kern<<<grid, 192, SMEM_BYTES, stream>>>(tmA, tmB, (const T*)bias, (T*)y, M, N, K);
+  dim3 grid((N + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), groups);
+  kern<<<grid, 192, SMEM_BYTES, stream>>>(tmA, tmB[0], tmB[1], tmB[2], gp, M, N, K);
   PAID_LAUNCH_CHECK("linear_tc_kernel");
   return PAID_OK;
 }
@@ -135,16 +146,28 @@ bool linear_tc_supported(long long M, int Nout, int K) {
   return M >= 1 && Nout % 8 == 0 && K % 8 == 0 && (M + BM - 1) / BM <= 65535;
 }
 
-int launch_linear_tc(const void* x, const void* w, const void* bias, void* y, long long M, int Nout, int K, int dtype,
-                     cudaStream_t stream) {
-  if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) return fail(PAID_EINVAL, "linear: pointers must be 16-byte aligned");
-  CUtensorMap tmA, tmB;
+int launch_linear_tc_grouped(const void* x, const void* const* w, const void* const* bias, void* const* y, int groups,
+                             long long M, int Nout, int K, int dtype, cudaStream_t stream) {
+  if (groups < 1 || groups > 3) return fail(PAID_EINVAL, "linear: 1..3 weight groups per launch");
+  CUtensorMap tmA, tmB[3];
+  GroupPtrs gp{};
+  if ((uintptr_t)x & 15) return fail(PAID_EINVAL, "linear: pointers must be 16-byte aligned");
   int st = make_tmap_2d(&tmA, x, dtype, M, K, K, BM);
   if (st != PAID_OK) return st;
-  st = make_tmap_2d(&tmB, w, dtype, Nout, K, K, BN);
-  if (st != PAID_OK) return st;
-  return dtype == PAID_F16 ? launch_t<__half>(tmA, tmB, bias, y, M, Nout, K, stream)
-                           : launch_t<__nv_bfloat16>(tmA, tmB, bias, y, M, Nout, K, stream);
+  for (int g = 0; g < 3; ++g) {
+    const int s = g < groups ? g : 0;  // unused slots repeat group 0 (any valid descriptor)
+    if (((uintptr_t)w[s] | (uintptr_t)y[s]) & 15) return fail(PAID_EINVAL, "linear: pointers must be 16-byte aligned");
+    if ((st = make_tmap_2d(&tmB[g], w[s], dtype, Nout, K, K, BN)) != PAID_OK) return st;
+    gp.bias[g] = bias ? bias[s] : nullptr;
+    gp.y[g] = y[s];
+  }
+  return dtype == PAID_F16 ? launch_t<__half>(tmA, tmB, gp, groups, M, Nout, K, stream)
+                           : launch_t<__nv_bfloat16>(tmA, tmB, gp, groups, M, Nout, K, stream);
+}
+
+int launch_linear_tc(const void* x, const void* w, const void* bias, void* y, long long M, int Nout, int K, int dtype,
+                     cudaStream_t stream) {
+  return launch_linear_tc_grouped(x, &w, bias ? &bias : nullptr, &y, 1, M, Nout, K, dtype, stream);
 }
 
 }  // namespace paid

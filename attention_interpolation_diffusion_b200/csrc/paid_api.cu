@@ -81,6 +81,18 @@ static int linear(const void* x, const void* w, const void* bias, void* y, long 
   return launch_linear_generic(x, w, bias, y, M, Nout, K, dtype, stream);
 }
 
+// up to three projections of the same input in one launch (q/k/v of self-attention, k/v of cross-attention)
+static int linear_grouped(const void* x, const void* const* w, void* const* y, int groups, long long M, int Nout, int K,
+                          int dtype, uint32_t flags, cudaStream_t stream) {
+  if (!(flags & PAID_FLAG_GENERIC_KERNELS) && linear_tc_supported(M, Nout, K))
+    return launch_linear_tc_grouped(x, w, nullptr, y, groups, M, Nout, K, dtype, stream);
+  for (int g = 0; g < groups; ++g) {
+    int st = launch_linear_generic(x, w[g], nullptr, y[g], M, Nout, K, dtype, stream);
+    if (st != PAID_OK) return st;
+  }
+  return PAID_OK;
+}
+
 // ---- measurement hook: CUDA events around the attention-core kernel ------------------------------
 struct ProfileState {
   std::mutex mu;
@@ -260,9 +272,9 @@ int paid_attn_project_endpoints(const PaidAttnParams* p, int32_t local_frame, vo
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   const char* src = p->ctx ? (const char*)p->ctx : (const char*)p->x;
   src += (long long)local_frame * p->L * p->Cc * 2;
-  st = linear(src, p->wk, nullptr, k_out, p->L, p->C, p->Cc, p->dtype, p->flags, stream);
-  if (st != PAID_OK) return st;
-  return linear(src, p->wv, nullptr, v_out, p->L, p->C, p->Cc, p->dtype, p->flags, stream);
+  const void* w[2] = {p->wk, p->wv};
+  void* y[2] = {k_out, v_out};
+  return linear_grouped(src, w, y, 2, p->L, p->C, p->Cc, p->dtype, p->flags, stream);
 }
 
 int paid_attn_forward(const PaidAttnParams* p, void* cuda_stream) {
@@ -280,9 +292,16 @@ int paid_attn_forward(const PaidAttnParams* p, void* cuda_stream) {
   const long long MS = (long long)p->N * p->S, ML = (long long)p->N * p->L;
 
   // interpolation.py:613, 623-624
-  if ((st = linear(p->x, p->wq, nullptr, Q, MS, p->C, p->C, p->dtype, p->flags, stream)) != PAID_OK) return st;
-  if ((st = linear(src, p->wk, nullptr, K, ML, p->C, p->Cc, p->dtype, p->flags, stream)) != PAID_OK) return st;
-  if ((st = linear(src, p->wv, nullptr, V, ML, p->C, p->Cc, p->dtype, p->flags, stream)) != PAID_OK) return st;
+  if (!p->ctx) {  // self-attention: q, k, v share the input -> one launch
+    const void* w[3] = {p->wq, p->wk, p->wv};
+    void* y[3] = {Q, K, V};
+    if ((st = linear_grouped(p->x, w, y, 3, MS, p->C, p->C, p->dtype, p->flags, stream)) != PAID_OK) return st;
+  } else {
+    if ((st = linear(p->x, p->wq, nullptr, Q, MS, p->C, p->C, p->dtype, p->flags, stream)) != PAID_OK) return st;
+    const void* w[2] = {p->wk, p->wv};
+    void* y[2] = {K, V};
+    if ((st = linear_grouped(src, w, y, 2, ML, p->C, p->Cc, p->dtype, p->flags, stream)) != PAID_OK) return st;
+  }
 
   CoreArgs a{};
   a.dtype = p->dtype; a.mode = p->mode; a.fused = p->fused ? 1 : 0;

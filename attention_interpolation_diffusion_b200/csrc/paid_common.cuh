@@ -140,6 +140,8 @@ int launch_linear_generic(const void* x, const void* w, const void* bias, void* 
                           int dtype, cudaStream_t stream);
 int launch_linear_tc(const void* x, const void* w, const void* bias, void* y, long long M, int Nout, int K,
                      int dtype, cudaStream_t stream);
+int launch_linear_tc_grouped(const void* x, const void* const* w, const void* const* bias, void* const* y, int groups,
+                             long long M, int Nout, int K, int dtype, cudaStream_t stream);
 bool linear_tc_supported(long long M, int Nout, int K);
 int launch_attn_generic(const CoreArgs& a, cudaStream_t stream);
 int launch_attn_tc(const CoreArgs& a, cudaStream_t stream);
