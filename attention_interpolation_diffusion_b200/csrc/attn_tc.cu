@@ -101,11 +101,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = frame_of_block(blockIdx.z, a.N), head = blockIdx.y, row0 = blockIdx.x * (QT * BM);
-  const float c = a.mode == PAID_PLAIN ? 0.f : a.coef[n];
-  const FramePlan plan = make_frame_plan(a.mode, a.fused, n, a.begin_frame, a.end_frame, c);
-  const Segments seg = make_segments(plan);
-  const int tiles = (a.L + BN - 1) / BN;
-  const int total_steps = seg.count * tiles;
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmQ);
@@ -130,6 +125,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = bar->tmem_slot;
+  ptx::pdl_launch_dependents();  // the next kernel may begin its prologue
+  ptx::pdl_wait();               // everything above overlapped the previous kernel's tail; its results are visible now
+
+  const float c = a.mode == PAID_PLAIN ? 0.f : a.coef[n];
+  const FramePlan plan = make_frame_plan(a.mode, a.fused, n, a.begin_frame, a.end_frame, c);
+  const Segments seg = make_segments(plan);
+  const int tiles = (a.L + BN - 1) / BN;
+  const int total_steps = seg.count * tiles;
 
   if (warp < 4) {
   ptx::setmaxnreg_dec<kRegsControl>();
@@ -378,7 +381,8 @@ int launch_t(const CUtensorMap* maps, const TcArgs& ta, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((ta.S + QT * BM - 1) / (QT * BM), ta.heads, ta.N);
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], ta);
+  PAID_CUDA_CHECK(launch_pdl(kern, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, maps[0], maps[1], maps[2], maps[3], maps[4],
+                             maps[5], maps[6], ta));
   PAID_LAUNCH_CHECK("attn_tc_kernel");
   return PAID_OK;
 }

@@ -60,6 +60,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  ptx::pdl_launch_dependents();  // the next kernel may begin its prologue
+  ptx::pdl_wait();               // ... and this one may not read its inputs before its predecessor is done
 
   if (warp == 0) {
     if (ptx::elect_one()) {
@@ -135,7 +137,7 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap* tmB, const GroupPtrs& gp
     configured = true;
   }
   dim3 grid((N + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), groups);
-  kern<<<grid, 192, SMEM_BYTES, stream>>>(tmA, tmB[0], tmB[1], tmB[2], gp, M, N, K);
+  PAID_CUDA_CHECK(launch_pdl(kern, grid, dim3(192), SMEM_BYTES, stream, tmA, tmB[0], tmB[1], tmB[2], gp, M, N, K));
   PAID_LAUNCH_CHECK("linear_tc_kernel");
   return PAID_OK;
 }
