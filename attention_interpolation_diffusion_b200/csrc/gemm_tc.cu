@@ -2,13 +2,16 @@
 //
 // Replaces attn.to_q / to_k / to_v / to_out[0] (reference interpolation.py:613, 623-624, 666).
 // Both operands are K-major, so x and w tiles are TMA-loaded as they lie in HBM (128-byte swizzle),
-// multiplied with tcgen05.mma (128x128x16 per instruction, fp32 accumulator in TMEM) and written back
+// multiplied with tcgen05.mma (128 x BN x 16 per instruction, fp32 accumulator in TMEM) and written back
 // by four epilogue warps straight from TMEM (+bias, -> fp16/bf16).
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2-5 epilogue.
-// One 128x128 output tile per CTA; 3-stage 32 KB ring so two CTAs share an SM and one CTA's epilogue
-// overlaps the other's main loop.  Up to three weight matrices that share the same input (q/k/v of a
-// self-attention layer, k/v of a cross-attention layer) run as ONE launch: blockIdx.z picks the group.
+// Persistent, warp-specialised: one CTA per SM walks the output tiles (n fastest, so concurrently running
+// CTAs share the same rows of x in L2).  warp 0 = TMA producer (4-stage ring), warp 1 = MMA issuer,
+// warps 2-5 = epilogue.  The TMEM accumulator is DOUBLE-BUFFERED (2 x BN columns): the epilogue of tile i
+// overlaps the main loop of tile i+1.  BN = 256 (SS-mode operand fetch per flop is half of a 128-wide tile:
+// the 1-CTA MMA is shared-memory-bandwidth bound) unless the output width is not a multiple of 256.
+// Up to three weight matrices that share the same input (q/k/v of a self-attention layer, k/v of a
+// cross-attention layer) run as ONE launch: the tile index also enumerates the group.
 #include <type_traits>
 
 #include "paid_common.cuh"
@@ -17,45 +20,48 @@
 namespace paid {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int TMEM_COLS = 128;
+constexpr int BM = 128, BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
 
 struct GroupPtrs {
   const void* bias[3];
   void* y[3];
 };
 
-template <typename T>
-__global__ void __launch_bounds__(192, 2)
+template <int BN> struct Cfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = A_BYTES + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+  static constexpr int kTmemCols = 2 * BN;  // two accumulators
+};
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(192, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
-                 const GroupPtrs gp, long long M, int N, int K) {
-  const int group = blockIdx.z;
-  const CUtensorMap& tmB = group == 0 ? tmB0 : (group == 1 ? tmB1 : tmB2);
-  const T* __restrict__ bias = (const T*)gp.bias[group];
-  T* __restrict__ y = (T*)gp.y[group];
+                 const GroupPtrs gp, long long M, int N, int K, int m_tiles, int n_tiles, int total_tiles) {
+  using C = Cfg<BN>;
+  constexpr int ST = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + ST * C::kStageBytes);
+  uint64_t* empty = full + ST;
+  uint64_t* acc_full = empty + ST;      // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;   // [2] epilogue -> MMA (4 warps arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const long long m0 = (long long)blockIdx.y * BM;
   const int num_kb = (K + BK - 1) / BK;
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmA);
-    ptx::prefetch_tmap(&tmB);
-    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-    ptx::mbar_init(tmem_full, 1);
+    ptx::prefetch_tmap(&tmB0);
+    for (int s = 0; s < ST; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 4); }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) { ptx::tmem_alloc(tmem_slot, TMEM_COLS); ptx::tmem_relinquish(); }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, C::kTmemCols); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -63,81 +69,119 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::pdl_launch_dependents();  // the next kernel may begin its prologue
   ptx::pdl_wait();               // ... and this one may not read its inputs before its predecessor is done
 
+  // tile -> (group, m block, n block); n fastest
+  auto decode = [&](int tile, int& group, long long& m0, int& n0) {
+    n0 = (tile % n_tiles) * BN;
+    const int r = tile / n_tiles;
+    m0 = (long long)(r % m_tiles) * BM;
+    group = r / m_tiles;
+  };
+
   if (warp == 0) {
     if (ptx::elect_one()) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        ptx::mbar_wait(&empty[s], ph ^ 1);
-        ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-        uint8_t* a = smem + s * STAGE_BYTES;
-        ptx::tma_load_2d(a, &tmA, &full[s], kb * BK, (int)m0);
-        ptx::tma_load_2d(a + A_BYTES, &tmB, &full[s], kb * BK, n0);
+      int kc = 0;  // k-blocks loaded so far (ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int group, n0; long long m0;
+        decode(tile, group, m0, n0);
+        const CUtensorMap* tmB = group == 0 ? &tmB0 : (group == 1 ? &tmB1 : &tmB2);
+        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          const int s = kc % ST;
+          ptx::mbar_wait(&empty[s], ((kc / ST) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[s], C::kStageBytes);
+          uint8_t* a = smem + s * C::kStageBytes;
+          ptx::tma_load_2d(a, &tmA, &full[s], kb * BK, (int)m0);
+          ptx::tma_load_2d(a + A_BYTES, tmB, &full[s], kb * BK, n0);
+          if (BN == 256) ptx::tma_load_2d(a + A_BYTES + 128 * BK * 2, tmB, &full[s], kb * BK, n0 + 128);
+        }
       }
     }
   } else if (warp == 1) {
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc(BM, BN, sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        ptx::mbar_wait(&full[s], ph);
+      constexpr uint32_t idesc = ptx::make_idesc(BM, BN, std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 0);
+      int kc = 0, tc = 0;  // k-blocks / tiles issued so far
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+        const int ab = tc & 1;  // accumulator buffer
+        ptx::mbar_wait(&acc_empty[ab], ((tc >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
-        const uint32_t a = ptx::smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t adesc = ptx::make_smem_desc_sw128(a, 16, 1024);
-        const uint64_t bdesc = ptx::make_smem_desc_sw128(a + A_BYTES, 16, 1024);
+        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          const int s = kc % ST;
+          ptx::mbar_wait(&full[s], (kc / ST) & 1);
+          ptx::tc_fence_after();
+          const uint32_t a = ptx::smem_u32(smem + s * C::kStageBytes);
+          const uint64_t adesc = ptx::make_smem_desc_sw128(a, 16, 1024);
+          const uint64_t bdesc = ptx::make_smem_desc_sw128(a + A_BYTES, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)  // +32 bytes per K step inside the 128-byte swizzle atom
-          ptx::mma_ss(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        ptx::tc_commit(&empty[s]);
+          for (int k = 0; k < BK / 16; ++k)  // +32 bytes per K step inside the 128-byte swizzle atom
+            ptx::mma_ss(tmem + ab * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          ptx::tc_commit(&empty[s]);
+        }
+        ptx::tc_commit(&acc_full[ab]);
       }
-      ptx::tc_commit(tmem_full);
     }
   } else {
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    ptx::mbar_wait(tmem_full, 0);
-    ptx::tc_fence_after();
-    const long long row = m0 + quad * 32 + lane;
+    int tc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+      int group, n0; long long m0;
+      decode(tile, group, m0, n0);
+      const T* __restrict__ bias = (const T*)gp.bias[group];
+      T* __restrict__ y = (T*)gp.y[group];
+      const int ab = tc & 1;
+      ptx::mbar_wait(&acc_full[ab], (tc >> 1) & 1);
+      ptx::tc_fence_after();
+      const long long row = m0 + quad * 32 + lane;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + c * 32, r);
-      ptx::tmem_wait_ld();
-      const int col0 = n0 + c * 32;
-      if (row < M && col0 < N) {
-        T* dst = y + row * N + col0;
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * BN + c * 32, r);
+        ptx::tmem_wait_ld();
+        const int col0 = n0 + c * 32;
+        if (row < M && col0 < N) {
+          T* dst = y + row * N + col0;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {  // 8 columns = 16 bytes per store
-          const int col = col0 + v * 8;
-          if (col >= N) break;
-          uint32_t o[4];
+          for (int v = 0; v < 4; ++v) {  // 8 columns = 16 bytes per store
+            const int col = col0 + v * 8;
+            if (col >= N) break;
+            uint32_t o[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float f0 = __uint_as_float(r[v * 8 + 2 * j]), f1 = __uint_as_float(r[v * 8 + 2 * j + 1]);
-            if (bias) { f0 += to_f32(bias[col + 2 * j]); f1 += to_f32(bias[col + 2 * j + 1]); }
-            o[j] = pack2<T>(f0, f1);
+            for (int j = 0; j < 4; ++j) {
+              float f0 = __uint_as_float(r[v * 8 + 2 * j]), f1 = __uint_as_float(r[v * 8 + 2 * j + 1]);
+              if (bias) { f0 += to_f32(bias[col + 2 * j]); f1 += to_f32(bias[col + 2 * j + 1]); }
+              o[j] = pack2<T>(f0, f1);
+            }
+            *reinterpret_cast<uint4*>(dst + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
           }
-          *reinterpret_cast<uint4*>(dst + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
+      // this accumulator buffer may be overwritten by the tile after next
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[ab]);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) { __syncwarp(); ptx::tmem_dealloc(tmem, TMEM_COLS); }
+  if (warp == 1) { __syncwarp(); ptx::tmem_dealloc(tmem, C::kTmemCols); }
 }
 
-template <typename T>
+template <typename T, int BN>
 int launch_t(const CUtensorMap& tmA, const CUtensorMap* tmB, const GroupPtrs& gp, int groups, long long M, int N, int K,
              cudaStream_t stream) {
-  auto kern = linear_tc_kernel<T>;
+  auto kern = linear_tc_kernel<T, BN>;
   static bool configured = false;
+  static int num_sms = 0;
   if (!configured) {
-    PAID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    PAID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
+    int dev = 0;
+    PAID_CUDA_CHECK(cudaGetDevice(&dev));
+    PAID_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
-  dim3 grid((N + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), groups);
-  PAID_CUDA_CHECK(launch_pdl(kern, grid, dim3(192), SMEM_BYTES, stream, tmA, tmB[0], tmB[1], tmB[2], gp, M, N, K));
+  const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = (N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles * groups;
+  dim3 grid(total < num_sms ? total : num_sms);
+  PAID_CUDA_CHECK(launch_pdl(kern, grid, dim3(192), Cfg<BN>::kSmemBytes, stream, tmA, tmB[0], tmB[1], tmB[2], gp, M, N, K,
+                             m_tiles, n_tiles, total));
   PAID_LAUNCH_CHECK("linear_tc_kernel");
   return PAID_OK;
 }
@@ -145,7 +189,7 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap* tmB, const GroupPtrs& gp
 }  // namespace
 
 bool linear_tc_supported(long long M, int Nout, int K) {
-  return M >= 1 && Nout % 8 == 0 && K % 8 == 0 && (M + BM - 1) / BM <= 65535;
+  return M >= 1 && Nout % 8 == 0 && K % 8 == 0 && (M + BM - 1) / BM < (1 << 22);
 }
 
 int launch_linear_tc_grouped(const void* x, const void* const* w, const void* const* bias, void* const* y, int groups,
@@ -159,12 +203,16 @@ int launch_linear_tc_grouped(const void* x, const void* const* w, const void* co
   for (int g = 0; g < 3; ++g) {
     const int s = g < groups ? g : 0;  // unused slots repeat group 0 (any valid descriptor)
     if (((uintptr_t)w[s] | (uintptr_t)y[s]) & 15) return fail(PAID_EINVAL, "linear: pointers must be 16-byte aligned");
-    if ((st = make_tmap_2d(&tmB[g], w[s], dtype, Nout, K, K, BN)) != PAID_OK) return st;
+    if ((st = make_tmap_2d(&tmB[g], w[s], dtype, Nout, K, K, 128)) != PAID_OK) return st;  // 128-row boxes
     gp.bias[g] = bias ? bias[s] : nullptr;
     gp.y[g] = y[s];
   }
-  return dtype == PAID_F16 ? launch_t<__half>(tmA, tmB, gp, groups, M, Nout, K, stream)
-                           : launch_t<__nv_bfloat16>(tmA, tmB, gp, groups, M, Nout, K, stream);
+  const bool wide = Nout % 256 == 0;
+  if (dtype == PAID_F16)
+    return wide ? launch_t<__half, 256>(tmA, tmB, gp, groups, M, Nout, K, stream)
+                : launch_t<__half, 128>(tmA, tmB, gp, groups, M, Nout, K, stream);
+  return wide ? launch_t<__nv_bfloat16, 256>(tmA, tmB, gp, groups, M, Nout, K, stream)
+              : launch_t<__nv_bfloat16, 128>(tmA, tmB, gp, groups, M, Nout, K, stream);
 }
 
 int launch_linear_tc(const void* x, const void* w, const void* bias, void* y, long long M, int Nout, int K, int dtype,
