@@ -26,6 +26,7 @@ EXPORTS = [
     "paid_attn_abi_version", "paid_attn_workspace_bytes", "paid_attn_core_workspace_bytes", "paid_attn_forward",
     "paid_attn_core", "paid_attn_project_endpoints", "paid_linear", "paid_attn_last_error",
     "paid_attn_launch_count", "paid_attn_last_kernel", "paid_attn_profile_enable", "paid_attn_profile_read",
+    "paid_geglu",
 ]
 
 
@@ -82,6 +83,8 @@ def load_library() -> C.CDLL:
     lib.paid_linear.restype = C.c_int
     lib.paid_linear.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                 C.c_int32, C.c_uint32, C.c_void_p]
+    lib.paid_geglu.restype = C.c_int
+    lib.paid_geglu.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.paid_attn_last_error.restype = C.c_char_p
     lib.paid_attn_launch_count.restype = C.c_uint64
     lib.paid_attn_last_kernel.restype = C.c_char_p
@@ -220,6 +223,16 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     _check(lib.paid_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), M, w.shape[0], K, _dtype_code(x),
                            flags, _stream(x)), "paid_linear")
     return y
+
+
+def geglu(h: torch.Tensor) -> torch.Tensor:
+    """a * gelu(g) for h = [a | g] along the last dim (``paid_geglu``)."""
+    lib = load_library()
+    _dev_check(h)
+    D = h.shape[-1] // 2
+    out = torch.empty(*h.shape[:-1], D, dtype=h.dtype, device=h.device)
+    _check(lib.paid_geglu(h.data_ptr(), out.data_ptr(), h.numel() // (2 * D), D, _dtype_code(h), _stream(h)), "paid_geglu")
+    return out
 
 
 def attn_core(q, k, v, coef, heads: int, mode: int, fused: bool, scale=None, begin_frame=None, end_frame=None,

@@ -105,6 +105,46 @@ int launch_lerp_endpoints(const void* kb, const void* vb, const void* ke, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// GEGLU: out[m, j] = h[m, j] * gelu(h[m, D + j]), exact erf GELU.  HBM-bound: 16-byte loads / stores,
+// 6 bytes of traffic per output element.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) geglu_kernel(const T* __restrict__ h, T* __restrict__ out, long long M, int D) {
+  const int vec_per_row = D / 8;
+  const long long total = M * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / vec_per_row;
+    const int j = (int)(i % vec_per_row) * 8;
+    const uint4 av = *reinterpret_cast<const uint4*>(h + m * 2 * D + j);
+    const uint4 gv = *reinterpret_cast<const uint4*>(h + m * 2 * D + D + j);
+    const T* a8 = reinterpret_cast<const T*>(&av);
+    const T* g8 = reinterpret_cast<const T*>(&gv);
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float g0 = to_f32(g8[2 * e]), g1 = to_f32(g8[2 * e + 1]);
+      const float r0 = to_f32(a8[2 * e]) * (0.5f * g0 * (1.f + erff(g0 * 0.70710678118654752f)));
+      const float r1 = to_f32(a8[2 * e + 1]) * (0.5f * g1 * (1.f + erff(g1 * 0.70710678118654752f)));
+      o[e] = pack2<T>(r0, r1);
+    }
+    *reinterpret_cast<uint4*>(out + m * D + j) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+int launch_geglu(const void* h, void* out, long long M, int D, int dtype, cudaStream_t stream) {
+  long long total = M * (D / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  if (dtype == PAID_F16)
+    geglu_kernel<__half><<<(unsigned)blocks, 256, 0, stream>>>((const __half*)h, (__half*)out, M, D);
+  else
+    geglu_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)h, (__nv_bfloat16*)out, M, D);
+  PAID_LAUNCH_CHECK("geglu_kernel");
+  return PAID_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic interpolated attention.  Block = 8 warps x 4 query rows; keys in tiles of 32 (lane = key);
 // output dims owned by lanes (j = lane + 32*jj).  Three slots with independent online-softmax state,
 // merged at the end (paid_common.cuh).

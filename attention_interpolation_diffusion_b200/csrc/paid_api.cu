@@ -223,6 +223,14 @@ int paid_linear(const void* x, const void* w, const void* bias, void* y, int64_t
   return linear(x, w, bias, y, M, Nout, K, dtype, flags, (cudaStream_t)cuda_stream);
 }
 
+int paid_geglu(const void* h, void* out, int64_t M, int32_t D, int32_t dtype, void* cuda_stream) {
+  if (!h || !out) return fail(PAID_EINVAL, "paid_geglu: h and out must be non-NULL");
+  if (M <= 0 || D <= 0 || D % 8) return fail(PAID_EINVAL, "paid_geglu: M > 0 and D a positive multiple of 8");
+  if (dtype != PAID_F16 && dtype != PAID_BF16) return fail(PAID_EINVAL, "paid_geglu: bad dtype");
+  if (((uintptr_t)h | (uintptr_t)out) & 15) return fail(PAID_EINVAL, "paid_geglu: pointers must be 16-byte aligned");
+  return launch_geglu(h, out, M, D, dtype, (cudaStream_t)cuda_stream);
+}
+
 int paid_attn_core(const PaidCoreParams* p, void* cuda_stream) {
   if (!p) return fail(PAID_EINVAL, "params is NULL");
   if (p->struct_size != sizeof(PaidCoreParams))

@@ -146,6 +146,7 @@ bool linear_tc_supported(long long M, int Nout, int K);
 int launch_attn_generic(const CoreArgs& a, cudaStream_t stream);
 int launch_attn_tc(const CoreArgs& a, cudaStream_t stream);
 bool attn_tc_supported(const CoreArgs& a);
+int launch_geglu(const void* h, void* out, long long M, int D, int dtype, cudaStream_t stream);
 int launch_lerp_endpoints(const void* kb, const void* vb, const void* ke, const void* ve, const float* coef,
                           void* kx, void* vx, int N, long long LC, int dtype, cudaStream_t stream);
 

@@ -137,6 +137,10 @@ int paid_attn_project_endpoints(const PaidAttnParams* p, int32_t local_frame, vo
 int paid_linear(const void* x, const void* w, const void* bias, void* y, int64_t M, int32_t Nout, int32_t K,
                 int32_t dtype, uint32_t flags, void* cuda_stream);
 
+/* GEGLU of the transformer block's feed-forward (the caller next to the attention path):
+ * h is (M, 2*D) = [a | g] per row (output of the first FF Linear), out (M, D) = a * gelu(g), exact (erf) GELU. */
+int paid_geglu(const void* h, void* out, int64_t M, int32_t D, int32_t dtype, void* cuda_stream);
+
 /* message for the last non-OK status returned on this thread ("" if none) */
 const char* paid_attn_last_error(void);
 

@@ -336,3 +336,12 @@ def test_ip_adapter_variants_n_frames(cabi):
         y = attn(dev(x), encoder_hidden_states=(dev(ctx), [dev(ip)])).float().cpu()
         assert cabi.last_kernel() == "tcgen05"
         check(y, fn(), (cls.__name__, "N=6"), rel=1e-3)
+
+
+def test_geglu_against_torch(cabi):
+    torch.manual_seed(2)
+    for M, D, dt in ((7 * 1024, 5120, torch.float16), (333, 2560, torch.float16), (64, 1280, torch.bfloat16)):
+        h = (torch.randn(M, 2 * D, device="cuda") * 2).to(dt)
+        ref = h[:, :D].float() * torch.nn.functional.gelu(h[:, D:].float())
+        out = cabi.geglu(h).float()
+        check(out.cpu(), ref.cpu(), ("geglu", M, D, dt), rel=1e-3 if dt == torch.float16 else 8e-3, maxabs=4e-2)
