@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--denoise-steps", type=int, default=STEPS_PER_SEQUENCE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly (for ncu launch lists)")
     return ap.parse_args()
 
 
@@ -212,7 +213,7 @@ def run_own_arm(args):
     dtype = torch.float16
     net = build_unet(args.model, dev, dtype, seed=1002)
     shard = FrameShard(rank, world, frames, None) if world > 1 else None
-    pipe = InterpolationPipeline(net, shard=shard)
+    pipe = InterpolationPipeline(net, shard=shard, use_cuda_graphs=not args.no_graphs)
     pipe.load_aid(t=None, is_fused=True, atype=args.atype, size=frames, alpha=4, beta=4)
     host = make_host_inputs(net.cfg, dtype)
     devin = {k: v.to(dev) for k, v in host.items()}
@@ -268,7 +269,7 @@ def run_own_arm(args):
     ms_eager = timed(step_dev, 1)
     _cabi.profile_enable(False)
     k_ms, k_launches, k_flops = _cabi.profile_read(reset=True)
-    pipe.use_cuda_graphs = True
+    pipe.use_cuda_graphs = not args.no_graphs
 
     if rank == 0:
         peak_tf, _, peak_src = peaks()
