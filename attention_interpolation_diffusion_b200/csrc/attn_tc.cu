@@ -299,15 +299,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const float neg = -m_ref * sl2;
         const float2 sl2v = make_float2(sl2, sl2), negv = make_float2(neg, neg);
         float2 sumA = make_float2(0.f, 0.f), sumB = make_float2(0.f, 0.f);
+        // Three phases over the 64 scores, each a run of independent instructions: packed FMAs (x * scale*log2e -
+        // max), then the MUFU.EX2 burst, then packed adds / converts.  While this warp sits in its SFU burst the
+        // other softmax warp of the scheduler runs its FMA/ALU phases, so the SFU stays busy.
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float2 x = ptx::fma2(make_float2(__uint_as_float(sr[h][e]), __uint_as_float(sr[h][e + 1])), sl2v, negv);
+            sr[h][e] = __float_as_uint(x.x); sr[h][e + 1] = __float_as_uint(x.y);
+          }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) sr[h][e] = __float_as_uint(ptx::ex2v(__uint_as_float(sr[h][e])));
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
-            // two packed fp32x2 FMAs (x * scale*log2e - max), four MUFU.EX2, two packed adds, two packed converts
-            float2 x0 = ptx::fma2(make_float2(__uint_as_float(sr[h][e]), __uint_as_float(sr[h][e + 1])), sl2v, negv);
-            float2 x1 = ptx::fma2(make_float2(__uint_as_float(sr[h][e + 2]), __uint_as_float(sr[h][e + 3])), sl2v, negv);
-            x0.x = ptx::ex2(x0.x); x0.y = ptx::ex2(x0.y); x1.x = ptx::ex2(x1.x); x1.y = ptx::ex2(x1.y);
+            const float2 x0 = make_float2(__uint_as_float(sr[h][e]), __uint_as_float(sr[h][e + 1]));
+            const float2 x1 = make_float2(__uint_as_float(sr[h][e + 2]), __uint_as_float(sr[h][e + 3]));
             sumA = ptx::add2(sumA, x0);
             sumB = ptx::add2(sumB, x1);
             pk[e / 2] = pack2<T>(x0.x, x0.y);

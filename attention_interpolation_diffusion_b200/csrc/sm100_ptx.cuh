@@ -24,6 +24,14 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// same, but volatile: keeps a run of exponentials together in program order (the compiler otherwise interleaves
+// each one with its dependent instructions, which serialises a warp on the SFU latency)
+__device__ __forceinline__ float ex2v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // packed fp32x2 arithmetic (sm_100: one FMA-pipe instruction for two lanes of data)
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
   float2 d;
