@@ -12,6 +12,7 @@
 // the 1-CTA MMA is shared-memory-bandwidth bound) unless the output width is not a multiple of 256.
 // Up to three weight matrices that share the same input (q/k/v of a self-attention layer, k/v of a
 // cross-attention layer) run as ONE launch: the tile index also enumerates the group.
+#include <cstdlib>
 #include <type_traits>
 
 #include "paid_common.cuh"
@@ -186,6 +187,165 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap* tmB, const GroupPtrs& gp
   return PAID_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.  Each
+// CTA loads 128 rows of x and HALF (128 rows) of the w tile, the leader CTA issues 256x256x16 MMAs that read
+// the operands of both CTAs, each CTA's TMEM receives its own 128 accumulator rows.  Per SM the operand
+// traffic through shared memory is halved relative to a 1-CTA 128x256 tile, which is what bounds that one.
+// ------------------------------------------------------------------------------------------------------
+constexpr int P_STAGES = 6;
+constexpr int P_STAGE_BYTES = A_BYTES + 128 * BK * 2;  // per CTA: 128 rows of x + 128 rows of w
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256;
+
+template <typename T>
+__global__ void __launch_bounds__(192, 1)
+linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                      const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
+                      const GroupPtrs gp, long long M, int N, int K, int m_tiles, int n_tiles, int total_tiles) {
+  constexpr int ST = P_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + ST * P_STAGE_BYTES);  // used in the leader CTA
+  uint64_t* empty = full + ST;                                              // per CTA (multicast commit)
+  uint64_t* acc_full = empty + ST;                                          // per CTA (multicast commit)
+  uint64_t* acc_empty = acc_full + 2;                                       // used in the leader CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB0);
+    for (int s = 0; s < ST; ++s) { ptx::mbar_init(&full[s], 2); ptx::mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 8); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // barriers and TMEM of both CTAs are ready
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+
+  auto decode = [&](int tile, int& group, long long& m0, int& n0) {
+    n0 = (tile % n_tiles) * 256;
+    const int r = tile / n_tiles;
+    m0 = (long long)(r % m_tiles) * 256;
+    group = r / m_tiles;
+  };
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int kc = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        int group, n0; long long m0;
+        decode(tile, group, m0, n0);
+        const CUtensorMap* tmB = group == 0 ? &tmB0 : (group == 1 ? &tmB1 : &tmB2);
+        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          const int s = kc % ST;
+          ptx::mbar_wait(&empty[s], ((kc / ST) & 1) ^ 1);  // this CTA's slot has been consumed
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * P_STAGE_BYTES);  // bytes of both CTAs
+          else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&full[s]), 0));
+          uint8_t* a = smem + s * P_STAGE_BYTES;
+          ptx::tma_load_2d_pair(a, &tmA, &full[s], kb * BK, (int)m0 + (int)rank * 128);
+          ptx::tma_load_2d_pair(a + A_BYTES, tmB, &full[s], kb * BK, n0 + (int)rank * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc(256, 256, std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 0);
+      int kc = 0, tc = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs, ++tc) {
+        const int ab = tc & 1;
+        ptx::mbar_wait(&acc_empty[ab], ((tc >> 1) & 1) ^ 1);  // the epilogues of both CTAs have drained it
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          const int s = kc % ST;
+          ptx::mbar_wait(&full[s], (kc / ST) & 1);
+          ptx::tc_fence_after();
+          const uint32_t a = ptx::smem_u32(smem + s * P_STAGE_BYTES);
+          const uint64_t adesc = ptx::make_smem_desc_sw128(a, 16, 1024);
+          const uint64_t bdesc = ptx::make_smem_desc_sw128(a + A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            ptx::mma_ss_pair(tmem + ab * 256, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          ptx::tc_commit_pair(&empty[s]);   // frees the slot in both CTAs
+        }
+        ptx::tc_commit_pair(&acc_full[ab]);  // both CTAs' epilogues may read their rows
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    int tc = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs, ++tc) {
+      int group, n0; long long m0;
+      decode(tile, group, m0, n0);
+      const T* __restrict__ bias = (const T*)gp.bias[group];
+      T* __restrict__ y = (T*)gp.y[group];
+      const int ab = tc & 1;
+      ptx::mbar_wait(&acc_full[ab], (tc >> 1) & 1);
+      ptx::tc_fence_after();
+      const long long row = m0 + rank * 128 + quad * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * 256 + c * 32, r);
+        ptx::tmem_wait_ld();
+        const int col0 = n0 + c * 32;
+        if (row < M) {
+          T* dst = y + row * N + col0;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int col = col0 + v * 8;
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float f0 = __uint_as_float(r[v * 8 + 2 * j]), f1 = __uint_as_float(r[v * 8 + 2 * j + 1]);
+              if (bias) { f0 += to_f32(bias[col + 2 * j]); f1 += to_f32(bias[col + 2 * j + 1]); }
+              o[j] = pack2<T>(f0, f1);
+            }
+            *reinterpret_cast<uint4*>(dst + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&acc_empty[ab]), 0));
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // neither CTA may exit (or free TMEM) while the other can still touch it
+  if (warp == 1) { __syncwarp(); ptx::tmem_dealloc_pair(tmem, 512); }
+}
+
+template <typename T>
+int launch_pair_t(const CUtensorMap& tmA, const CUtensorMap* tmB, const GroupPtrs& gp, int groups, long long M, int N,
+                  int K, cudaStream_t stream) {
+  auto kern = linear_tc_pair_kernel<T>;
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    PAID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    int dev = 0;
+    PAID_CUDA_CHECK(cudaGetDevice(&dev));
+    PAID_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    configured = true;
+  }
+  const int m_tiles = (int)((M + 255) / 256), n_tiles = N / 256;
+  const int total = m_tiles * n_tiles * groups;
+  int pairs = num_sms / 2;
+  if (total < pairs) pairs = total;
+  PAID_CUDA_CHECK(launch_pdl_pairs(kern, dim3(2 * pairs), dim3(192), P_SMEM_BYTES, stream, tmA, tmB[0], tmB[1], tmB[2], gp,
+                                   M, N, K, m_tiles, n_tiles, total));
+  PAID_LAUNCH_CHECK("linear_tc_pair_kernel");
+  return PAID_OK;
+}
+
 }  // namespace
 
 bool linear_tc_supported(long long M, int Nout, int K) {
@@ -208,6 +368,9 @@ int launch_linear_tc_grouped(const void* x, const void* const* w, const void* co
     gp.y[g] = y[s];
   }
   const bool wide = Nout % 256 == 0;
+  if (wide && M >= 256 && !getenv("PAID_NO_CTA_PAIRS"))
+    return dtype == PAID_F16 ? launch_pair_t<__half>(tmA, tmB, gp, groups, M, Nout, K, stream)
+                             : launch_pair_t<__nv_bfloat16>(tmA, tmB, gp, groups, M, Nout, K, stream);
   if (dtype == PAID_F16)
     return wide ? launch_t<__half, 256>(tmA, tmB, gp, groups, M, Nout, K, stream)
                 : launch_t<__half, 128>(tmA, tmB, gp, groups, M, Nout, K, stream);

@@ -123,9 +123,15 @@ def test_properties_at_full_size(cabi, m, fused):
     check(y3, yg, "default kernels == generic kernels", rel=1e-3)
 
 
-def test_linear_against_torch(cabi):
+@pytest.mark.parametrize("pairs", [True, False], ids=["cta_pairs", "single_cta"])
+def test_linear_against_torch(cabi, pairs, monkeypatch):
+    """Projection GEMM: the cta_group::2 CTA-pair kernel (256-wide outputs, M >= 256), the 1-CTA 128x256 / 128x128
+    kernels (PAID_NO_CTA_PAIRS forces them) and the generic kernel, ragged M / N / K included."""
+    if not pairs:
+        monkeypatch.setenv("PAID_NO_CTA_PAIRS", "1")
     torch.manual_seed(0)
-    for M, Nout, K in ((7 * 1024, 1280, 1280), (539, 640, 2048), (77, 320, 768), (4096, 320, 320), (1000, 72, 200)):
+    for M, Nout, K in ((7 * 1024, 1280, 1280), (300, 1280, 2048), (539, 640, 2048), (77, 320, 768), (4096, 320, 320),
+                       (1000, 72, 200), (7 * 77, 1280, 2048)):
         x = torch.randn(M, K, device="cuda").half()
         w = (torch.randn(Nout, K, device="cuda") / K ** 0.5).half()
         b = torch.randn(Nout, device="cuda").half()
