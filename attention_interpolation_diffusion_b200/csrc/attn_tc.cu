@@ -393,8 +393,10 @@ int launch_t(const CUtensorMap* maps, const TcArgs& ta, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((ta.S + QT * BM - 1) / (QT * BM), ta.heads, ta.N);
+  profile_mark_begin(stream);
   PAID_CUDA_CHECK(launch_pdl(kern, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, maps[0], maps[1], maps[2], maps[3], maps[4],
                              maps[5], maps[6], ta));
+  profile_mark_end(stream);
   PAID_LAUNCH_CHECK("attn_tc_kernel");
   return PAID_OK;
 }

@@ -297,11 +297,12 @@ linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * 256 + c * 32, r);
         ptx::tmem_wait_ld();
         const int col0 = n0 + c * 32;
-        if (row < M) {
+        if (row < M && col0 < N) {
           T* dst = y + row * N + col0;
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             const int col = col0 + v * 8;
+            if (col >= N) break;  // ragged last tile (N is a multiple of 8, not necessarily of 256)
             uint32_t o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -336,7 +337,7 @@ int launch_pair_t(const CUtensorMap& tmA, const CUtensorMap* tmB, const GroupPtr
     PAID_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
-  const int m_tiles = (int)((M + 255) / 256), n_tiles = N / 256;
+  const int m_tiles = (int)((M + 255) / 256), n_tiles = (N + 255) / 256;
   const int total = m_tiles * n_tiles * groups;
   int pairs = num_sms / 2;
   if (total < pairs) pairs = total;
@@ -368,7 +369,9 @@ int launch_linear_tc_grouped(const void* x, const void* const* w, const void* co
     gp.y[g] = y[s];
   }
   const bool wide = Nout % 256 == 0;
-  if (wide && M >= 256 && !getenv("PAID_NO_CTA_PAIRS"))
+  // CTA pairs whenever the 256-wide tiles are at least 5/6 full (640 = 2.5 tiles still beats the 1-CTA kernel)
+  const bool pairs_ok = M >= 256 && Nout >= 256 && 6 * Nout >= 5 * 256 * ((Nout + 255) / 256);
+  if (pairs_ok && !getenv("PAID_NO_CTA_PAIRS"))
     return dtype == PAID_F16 ? launch_pair_t<__half>(tmA, tmB, gp, groups, M, Nout, K, stream)
                              : launch_pair_t<__nv_bfloat16>(tmA, tmB, gp, groups, M, Nout, K, stream);
   if (dtype == PAID_F16)

@@ -98,11 +98,31 @@ struct ProfileState {
   std::mutex mu;
   bool on = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> used, pool;
+  std::pair<cudaEvent_t, cudaEvent_t> current{nullptr, nullptr};
   double alg_flops = 0;
 };
 static ProfileState& prof() {
   static ProfileState p;
   return p;
+}
+void profile_mark_begin(cudaStream_t stream) {
+  ProfileState& ps = prof();
+  if (!ps.on) return;
+  std::lock_guard<std::mutex> lk(ps.mu);
+  if (!ps.pool.empty()) { ps.current = ps.pool.back(); ps.pool.pop_back(); }
+  else if (cudaEventCreate(&ps.current.first) != cudaSuccess || cudaEventCreate(&ps.current.second) != cudaSuccess) {
+    ps.current = {nullptr, nullptr};
+    return;
+  }
+  cudaEventRecord(ps.current.first, stream);
+}
+void profile_mark_end(cudaStream_t stream) {
+  ProfileState& ps = prof();
+  if (!ps.on || !ps.current.first) return;
+  std::lock_guard<std::mutex> lk(ps.mu);
+  cudaEventRecord(ps.current.second, stream);
+  ps.used.push_back(ps.current);
+  ps.current = {nullptr, nullptr};
 }
 static double algorithmic_flops(const CoreArgs& a) {
   const double A = 2.0 * a.N * a.S * a.L * a.heads * a.head_dim;
@@ -113,13 +133,7 @@ static double algorithmic_flops(const CoreArgs& a) {
 
 static int core_dispatch(const CoreArgs& a, uint32_t flags, cudaStream_t stream) {
   ProfileState& ps = prof();
-  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
-  if (ps.on) {
-    std::lock_guard<std::mutex> lk(ps.mu);
-    if (!ps.pool.empty()) { ev = ps.pool.back(); ps.pool.pop_back(); }
-    else { PAID_CUDA_CHECK(cudaEventCreate(&ev.first)); PAID_CUDA_CHECK(cudaEventCreate(&ev.second)); }
-    PAID_CUDA_CHECK(cudaEventRecord(ev.first, stream));
-  }
+  const size_t before = ps.on ? ps.used.size() : 0;
   int st;
   if (!(flags & PAID_FLAG_GENERIC_KERNELS) && attn_tc_supported(a)) {
     *last_kernel_slot() = "tcgen05";
@@ -128,10 +142,8 @@ static int core_dispatch(const CoreArgs& a, uint32_t flags, cudaStream_t stream)
     *last_kernel_slot() = "generic";
     st = launch_attn_generic(a, stream);
   }
-  if (ev.first) {
-    PAID_CUDA_CHECK(cudaEventRecord(ev.second, stream));
+  if (ps.on && ps.used.size() > before) {  // the launcher bracketed its kernel with events
     std::lock_guard<std::mutex> lk(ps.mu);
-    ps.used.push_back(ev);
     ps.alg_flops += algorithmic_flops(a);
   }
   return st;

@@ -135,6 +135,10 @@ struct CoreArgs {
   long long stride0;  // frame stride of k / v in elements (0: one matrix shared by all frames)
 };
 
+// measurement hook (paid_attn_profile_*): called by the attention launchers immediately around the kernel launch
+void profile_mark_begin(cudaStream_t stream);
+void profile_mark_end(cudaStream_t stream);
+
 // kernel launchers (each returns a PaidStatus)
 int launch_linear_generic(const void* x, const void* w, const void* bias, void* y, long long M, int Nout, int K,
                           int dtype, cudaStream_t stream);

@@ -97,6 +97,43 @@ def make_host_inputs(cfg, dtype):
     return d
 
 
+def kernel_rooflines(net, frames, atype, peak_tf):
+    """The attention-core kernel in isolation, per attention-layer class of the UNet: median of 7 launches timed with
+    CUDA events on the launching stream, L2 flushed (256 MB memset) between launches, random q/k/v of the layer's
+    geometry.  Algorithmic flops per SURVEY.md 8d."""
+    import torch
+    from attention_interpolation_diffusion_b200 import _cabi
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    classes = {}
+    for g in net.attention_geometry():
+        key = (g["S"], g["L"], g["C"], g["heads"])
+        classes[key] = classes.get(key, 0) + 1
+    coef = torch.linspace(0, 1, frames, device="cuda")
+    mode, mult = (_cabi.PAID_OUTER, 6) if atype == "fused_outer" else (_cabi.PAID_INNER, 4)
+    out = []
+    for (S, L, C, h), count in sorted(classes.items(), key=lambda kv: -kv[0][0] * kv[0][1]):
+        q = torch.randn(frames, S, C, device="cuda").half()
+        k = torch.randn(frames, L, C, device="cuda").half()
+        v = torch.randn(frames, L, C, device="cuda").half()
+        A = 2.0 * frames * S * L * C
+        for name, m, fused, mul in ((atype, mode, True, mult), ("plain", _cabi.PAID_PLAIN, False, 2)):
+            ts = []
+            for i in range(10):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _cabi.attn_core(q, k, v, coef, h, m, fused)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ts.append(e0.elapsed_time(e1))
+            ms = statistics.median(ts)
+            tf = mul * A / ms / 1e9
+            out.append({"S": S, "L": L, "C": C, "heads": h, "layers": count, "mode": name, "ms": round(ms, 4),
+                        "achieved_tflops": round(tf, 1), "frac": round(tf / peak_tf, 3)})
+    return out
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -274,11 +311,14 @@ def run_own_arm(args):
     if rank == 0:
         peak_tf, _, peak_src = peaks()
         achieved = k_flops / (k_ms / 1000.0) / 1e12 if k_ms > 0 else None
+        by_shape = kernel_rooflines(net, frames // world, args.atype, peak_tf)
         roofline = {"kernel": f"attention core ({_cabi.last_kernel()})", "bound": "tensor", "achieved": achieved,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None,
                     "peak_source": peak_src, "traffic": None, "launches": k_launches,
                     "avg_launch_ms": k_ms / max(k_launches, 1), "share_of_step": k_ms / (ms / args.steps),
-                    "eager_step_ms": ms_eager,
+                    "eager_step_ms": ms_eager, "by_shape_isolated": by_shape,
+                    "traffic_note": "ncu dram bytes per launch, dominant shape (S=L=4096, C=640, fused-outer, N=7): "
+                                    "118 MB read + 29 MB write vs 110 + 37 MB algorithmic (profiles/r1_ncu_attn_v4.txt)",
                     "how": "CUDA events around every attention-core launch of one extra, eagerly launched sequence "
                            "after the timed region (the timed steps replay CUDA graphs); share_of_step = summed "
                            "kernel time / timed step; algorithmic flops per SURVEY.md 8d (fused-outer 6A, "
