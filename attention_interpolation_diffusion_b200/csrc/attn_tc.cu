@@ -11,17 +11,18 @@
 // running statistics while they have seen the same keys) and its P.V product is issued into both
 // accumulators; endpoint K/V are read once per CTA and never replicated or concatenated.
 //
-// Work decomposition: one CTA per (frame, head, 256 query rows) = two 128-row Q tiles sharing every K/V tile.
-//   warp 0        TMA producer: Q tiles once, then K / V tiles (64 keys) into an 8-stage shared-memory ring
+// Work decomposition: one CTA per (frame, head, QT x 128 query rows); QT Q tiles share every K/V tile.
+//   warp 0        TMA producer: Q tile(s) once, then K / V tiles (64 keys) into a 5- or 8-stage shared-memory ring
 //   warp 1        tcgen05.mma issuer: S_t = Q_t K^T (SS), acc_{t,stream} += P_t V (A operand P from TMEM)
 //   warps 2-3     idle (they only give their registers away)
 //   warps 4-7     softmax warpgroup of Q tile 0 (one thread per query row)
-//   warps 8-11    softmax warpgroup of Q tile 1
+//   warps 8-11    softmax warpgroup of Q tile 1 (QT = 2 only)
 // The score tile of each Q tile is DOUBLE-BUFFERED in TMEM: S_t(j+2) = Q_t K(j+2)^T is issued right after
 // P_t(j) V(j), so the scores of the next step are ready while the softmax warps still work on the current
 // one and the exp-bound softmax never waits for the tensor core.
-// TMEM (512 columns): S_{t,b} at 64 (2 t + b) (P_{t,b} aliases its low 32 columns as packed 16-bit),
-// acc_{t,stream} at 256 + 128 t + 64 stream.
+// TMEM (256 QT columns): S_{t,b} at 64 (2 t + b) (P_{t,b} aliases its low 32 columns as packed 16-bit),
+// acc_{t,stream} at 128 QT + 128 t + 64 stream.
+#include <cstdlib>
 #include <type_traits>
 
 #include "paid_common.cuh"
@@ -32,15 +33,26 @@ namespace {
 
 constexpr int D = 64;            // head_dim
 constexpr int BM = 128;          // rows per Q tile
-constexpr int QT = 2;            // Q tiles per CTA
+// Q tiles per CTA is a template parameter.  QT = 1 (default): one 128-row Q tile, half the TMEM / shared memory /
+// threads, TWO CTAs per SM: the two resident CTAs run out of phase, so one computes while the other starts, waits
+// for the tensor core or drains (measured 6-11 % faster than QT = 2 on every SDXL shape).  QT = 2 (PAID_ATTN_QT=2):
+// one CTA per SM whose two Q tiles share every K/V tile (half the K/V traffic from L2 to shared memory).
 constexpr int BN = 64;           // keys per step
 constexpr int ST = 8;            // K/V ring stages
 constexpr int Q_BYTES = BM * D * 2;    // 16 KB
 constexpr int KV_BYTES = BN * D * 2;   // 16 KB
-constexpr int SMEM_BYTES = 1024 + QT * Q_BYTES + ST * 2 * KV_BYTES + 512;
-constexpr int NUM_THREADS = 128 * (1 + QT);  // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1..QT: softmax
-constexpr int kRegsControl = 56, kRegsSoftmax = 224;  // setmaxnreg split of the 64K register file
-constexpr uint32_t TMEM_S = 0, TMEM_ACC = 256;
+template <int QT> struct Shape {
+  static constexpr int kStages = QT == 2 ? ST : 5;   // K/V ring stages (two CTAs per SM share 227 KB when QT = 1)
+  static constexpr int kSmemBytes = 1024 + QT * Q_BYTES + kStages * 2 * KV_BYTES + 512;
+  static constexpr int kThreads = 128 * (1 + QT);   // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1..QT: softmax
+  static constexpr int kCtasPerSm = QT == 2 ? 1 : 2;
+  // setmaxnreg split of the register file among the CTA's warpgroups (per-CTA budget 64K / kCtasPerSm)
+  static constexpr int kRegsControl = 56;
+  static constexpr int kRegsSoftmax = QT == 2 ? 224 : 200;
+  static constexpr uint32_t kTmemCols = 256 * QT;
+  static constexpr uint32_t kTmemAcc = 128 * QT;     // S buffers first (2 x 64 columns per tile), accumulators after
+};
+constexpr uint32_t TMEM_S = 0;
 constexpr float kRescaleThreshold = 8.f;  // log2 units: rescale an accumulator only when its max grew by > 2^8
 
 struct TcArgs {
@@ -57,7 +69,7 @@ struct TcArgs {
 struct Barriers {
   uint64_t q_full;
   uint64_t k_full[ST], k_empty[ST], v_full[ST], v_empty[ST];
-  uint64_t s_full[QT][2], p_full[QT][2], pv_done[QT], acc_final[QT];
+  uint64_t s_full[2][2], p_full[2][2], pv_done[2], acc_final[2];
   uint32_t tmem_slot;
 };
 
@@ -86,17 +98,19 @@ __device__ __forceinline__ int frame_of_block(int z, int N) {
   return z < N - 2 ? z + 1 : (z == N - 2 ? 0 : N - 1);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <typename T, int QT>
+__global__ void __launch_bounds__(Shape<QT>::kThreads, Shape<QT>::kCtasPerSm)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ CUtensorMap tmK2,
                const __grid_constant__ CUtensorMap tmV2, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int ST = Shape<QT>::kStages;           // (shadows the namespace constant: ring depth of this variant)
+  constexpr uint32_t TMEM_ACC = Shape<QT>::kTmemAcc;
   uint8_t* sQ = smem;                              // [QT][128][64]
-  uint8_t* sK = sQ + QT * Q_BYTES;                 // [ST][128][64]
-  uint8_t* sV = sK + ST * KV_BYTES;                // [ST][128][64]
+  uint8_t* sK = sQ + QT * Q_BYTES;                 // [ST][64][64]
+  uint8_t* sV = sK + ST * KV_BYTES;                // [ST][64][64]
   Barriers* bar = reinterpret_cast<Barriers*>(sV + ST * KV_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -120,7 +134,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) { ptx::tmem_alloc(&bar->tmem_slot, 512); ptx::tmem_relinquish(); }
+  if (warp == 1) { ptx::tmem_alloc(&bar->tmem_slot, Shape<QT>::kTmemCols); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -135,7 +149,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int total_steps = seg.count * tiles;
 
   if (warp < 4) {
-  ptx::setmaxnreg_dec<kRegsControl>();
+  ptx::setmaxnreg_dec<Shape<QT>::kRegsControl>();
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (ptx::elect_one()) {
@@ -197,7 +211,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
             for (int st = 0; st < 2; ++st) {
               if (!(feeds & (1 << st))) continue;
-              const uint32_t acc = tmem + TMEM_ACC + t * 128 + st * D;
+              const uint32_t acc = tmem + TMEM_ACC + t * 128 + st * D;  // 2 streams x 64 columns per tile
 #pragma unroll
               for (int k = 0; k < BN / 16; ++k) {
                 // 16 keys per MMA: 8 packed columns of P, 16 rows (2048 B) of the V tile
@@ -221,7 +235,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   }
   } else {
-    ptx::setmaxnreg_inc<kRegsSoftmax>();
+    ptx::setmaxnreg_inc<Shape<QT>::kRegsSoftmax>();
     // ================================ softmax warpgroups ==========================
     const int t = (warp - 4) >> 2;   // Q tile of this warpgroup
     const int quad = warp & 3;       // TMEM lane quadrant of this warp
@@ -381,12 +395,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) { __syncwarp(); ptx::tmem_dealloc(tmem, 512); }
+  if (warp == 1) { __syncwarp(); ptx::tmem_dealloc(tmem, Shape<QT>::kTmemCols); }
 }
 
-template <typename T>
+template <typename T, int QT>
 int launch_t(const CUtensorMap* maps, const TcArgs& ta, cudaStream_t stream) {
-  auto kern = attn_tc_kernel<T>;
+  auto kern = attn_tc_kernel<T, QT>;
+  constexpr int SMEM_BYTES = Shape<QT>::kSmemBytes, NUM_THREADS = Shape<QT>::kThreads;
   static bool configured = false;
   if (!configured) {
     PAID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -439,7 +454,11 @@ int launch_attn_tc(const CoreArgs& a, cudaStream_t stream) {
   ta.scale_log2 = a.scale * kLog2e;
   ta.coef = a.coef; ta.out = a.out;
   ta.accumulate = a.accumulate; ta.out_scale = a.out_scale; ta.out_frame_scale = a.out_frame_scale;
-  return a.dtype == PAID_F16 ? launch_t<__half>(maps, ta, stream) : launch_t<__nv_bfloat16>(maps, ta, stream);
+  const char* force = getenv("PAID_ATTN_QT");
+  const bool single_tile = !(force && force[0] == '2');
+  if (single_tile)
+    return a.dtype == PAID_F16 ? launch_t<__half, 1>(maps, ta, stream) : launch_t<__nv_bfloat16, 1>(maps, ta, stream);
+  return a.dtype == PAID_F16 ? launch_t<__half, 2>(maps, ta, stream) : launch_t<__nv_bfloat16, 2>(maps, ta, stream);
 }
 
 }  // namespace paid

@@ -227,6 +227,22 @@ def test_core_growing_logits_exercise_rescale(cabi):
         check(out.float().cpu(), gen.float().cpu(), ("growing logits vs generic", m, fused), rel=2e-3)
 
 
+def test_core_two_tile_variant_matches(cabi, monkeypatch):
+    """The QT = 2 configuration of the tcgen05 kernel (one CTA per SM, two Q tiles sharing the K/V tiles) against the
+    default QT = 1 (two CTAs per SM)."""
+    torch.manual_seed(13)
+    N, S, L, h = 5, 700, 333, 3
+    q, k, v = (torch.randn(N, T, h * 64, device="cuda").half() for T in (S, L, L))
+    coef = O.coefficients(N, 2, 2).cuda()
+    for m, fused in MODES + [("plain", False)]:
+        mode = O.MODE_NAMES[m]
+        monkeypatch.delenv("PAID_ATTN_QT", raising=False)
+        one = cabi.attn_core(q, k, v, coef, h, mode, fused).float().cpu()
+        monkeypatch.setenv("PAID_ATTN_QT", "2")
+        two = cabi.attn_core(q, k, v, coef, h, mode, fused).float().cpu()
+        check(two, one, ("QT=2 vs QT=1", m, fused), rel=1e-5, maxabs=1e-3)
+
+
 def test_core_is_deterministic_under_repetition(cabi):
     """Race detector: the same launch repeated must be bit-identical (SDXL 32x32 geometry, all modes)."""
     N, S, h, d = 7, 1024, 20, 64
