@@ -1,4 +1,5 @@
-// Interpolated attention core on the 5th-generation tensor cores (head_dim 64).
+// Interpolated attention core on the 5th-generation tensor cores (head_dim 64, or any multiple of 8 below 64
+// zero-padded to 64 by the TMA unit: SD1.5's 64x64 level has head_dim 40).
 //
 // Replaces, per attention layer, the reference's endpoint replication, head split, [self ; endpoint]
 // concatenations, the two materialised softmax(QK^T) matrices, the two P.V products and the alpha-lerp
@@ -31,7 +32,10 @@
 namespace paid {
 namespace {
 
-constexpr int D = 64;            // head_dim
+constexpr int D = 64;            // head_dim of the tiles.  A smaller head_dim (multiple of 8) runs zero-padded: the 4-D
+                                 // tensor maps have extent head_dim in their innermost dimension and a 64-wide box, so
+                                 // the TMA unit fills columns head_dim..63 of every Q/K/V tile with zeros (scores and
+                                 // the first head_dim accumulator columns are exact); the epilogue stores head_dim columns.
 constexpr int BM = 128;          // rows per Q tile
 // Q tiles per CTA is a template parameter.  QT = 1 (default): one 128-row Q tile, half the TMEM / shared memory /
 // threads, TWO CTAs per SM: the two resident CTAs run out of phase, so one computes while the other starts, waits
@@ -56,7 +60,7 @@ constexpr uint32_t TMEM_S = 0;
 constexpr float kRescaleThreshold = 8.f;  // log2 units: rescale an accumulator only when its max grew by > 2^8
 
 struct TcArgs {
-  int mode, fused, N, S, L, heads, begin_frame, end_frame;
+  int mode, fused, N, S, L, heads, head_dim, begin_frame, end_frame;
   float scale_log2;
   const float* coef;
   void* out;
@@ -360,7 +364,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const float cf[2] = {seg.a_active ? os * plan.wA / l_st[0] : 0.f, seg.b_active ? os * plan.wB / l_st[1] : 0.f};
     const bool active[2] = {seg.a_active, seg.b_active};
     const int row = row0 + t * BM + quad * 32 + lane;
-    T* dst = (T*)a.out + ((long long)n * a.S + row) * (a.heads * D) + head * D;
+    T* dst = (T*)a.out + ((long long)n * a.S + row) * (a.heads * a.head_dim) + head * a.head_dim;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float acc[32];
@@ -379,6 +383,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (a.accumulate) {  // out += ...: the IP-Adapter second attention (CTA-uniform branch)
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
+            if (h * 32 + v * 8 >= a.head_dim) break;
             const uint4 old = *reinterpret_cast<const uint4*>(dst + h * 32 + v * 8);
             const T* o8 = reinterpret_cast<const T*>(&old);
 #pragma unroll
@@ -387,9 +392,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
 #pragma unroll
         for (int v = 0; v < 4; ++v)
-          *reinterpret_cast<uint4*>(dst + h * 32 + v * 8) =
-              make_uint4(pack2<T>(acc[v * 8], acc[v * 8 + 1]), pack2<T>(acc[v * 8 + 2], acc[v * 8 + 3]),
-                         pack2<T>(acc[v * 8 + 4], acc[v * 8 + 5]), pack2<T>(acc[v * 8 + 6], acc[v * 8 + 7]));
+          if (h * 32 + v * 8 < a.head_dim)  // padded head_dim: columns head_dim..63 are zero and are not stored
+            *reinterpret_cast<uint4*>(dst + h * 32 + v * 8) =
+                make_uint4(pack2<T>(acc[v * 8], acc[v * 8 + 1]), pack2<T>(acc[v * 8 + 2], acc[v * 8 + 3]),
+                           pack2<T>(acc[v * 8 + 4], acc[v * 8 + 5]), pack2<T>(acc[v * 8 + 6], acc[v * 8 + 7]));
       }
     }
   }
@@ -419,19 +425,23 @@ int launch_t(const CUtensorMap* maps, const TcArgs& ta, cudaStream_t stream) {
 }  // namespace
 
 bool attn_tc_supported(const CoreArgs& a) {
-  return a.head_dim == D && a.heads <= 65535 && a.N <= 65535 &&
+  const char* nopad = getenv("PAID_ATTN_NO_PAD");   // debugging: serve head_dim < 64 with the generic kernel
+  const bool padded_ok = a.head_dim < D && a.head_dim >= 16 && a.head_dim % 8 == 0 && !(nopad && nopad[0] == '1');
+  return (a.head_dim == D || padded_ok) && a.heads <= 65535 && a.N <= 65535 &&
          !(((uintptr_t)a.q | (uintptr_t)a.k | (uintptr_t)a.v | (uintptr_t)a.out | (uintptr_t)a.k1 | (uintptr_t)a.v1 |
             (uintptr_t)a.k2 | (uintptr_t)a.v2) & 15);
 }
 
 int launch_attn_tc(const CoreArgs& a, cudaStream_t stream) {
   CUtensorMap maps[7];
-  const long long C = (long long)a.heads * D;
-  int st = make_tmap_heads(&maps[0], a.q, a.dtype, a.N, a.S, a.heads, D, (long long)a.S * C, BM);
-  if (st != PAID_OK) return st;
+  const int hd = a.head_dim;  // <= D; the box of every map is D wide (zero fill beyond hd)
+  const long long C = (long long)a.heads * hd;
+  int st = make_tmap_heads(&maps[0], a.q, a.dtype, a.N, a.S, a.heads, hd, (long long)a.S * C, BM);
+  // a driver that rejects a box wider than the tensor: nothing was launched, the caller falls back (core_dispatch)
+  if (st != PAID_OK) return hd < D ? PAID_EUNSUPPORTED : st;
   const long long kv_frames = a.stride0 ? a.N : 1;
-  if ((st = make_tmap_heads(&maps[1], a.k, a.dtype, kv_frames, a.L, a.heads, D, a.stride0, BN)) != PAID_OK) return st;
-  if ((st = make_tmap_heads(&maps[2], a.v, a.dtype, kv_frames, a.L, a.heads, D, a.stride0, BN)) != PAID_OK) return st;
+  if ((st = make_tmap_heads(&maps[1], a.k, a.dtype, kv_frames, a.L, a.heads, hd, a.stride0, BN)) != PAID_OK) return st;
+  if ((st = make_tmap_heads(&maps[2], a.v, a.dtype, kv_frames, a.L, a.heads, hd, a.stride0, BN)) != PAID_OK) return st;
   TcArgs ta{};
   ta.per_frame[0] = a.stride0 ? 1 : 0;
   const void* kk[2] = {a.k1, a.k2};
@@ -440,8 +450,8 @@ int launch_attn_tc(const CoreArgs& a, cudaStream_t stream) {
   for (int s = 0; s < 2; ++s) {
     if (kk[s]) {
       const long long frames = strides[s] ? a.N : 1;
-      if ((st = make_tmap_heads(&maps[3 + 2 * s], kk[s], a.dtype, frames, a.L, a.heads, D, strides[s], BN)) != PAID_OK) return st;
-      if ((st = make_tmap_heads(&maps[4 + 2 * s], vv[s], a.dtype, frames, a.L, a.heads, D, strides[s], BN)) != PAID_OK) return st;
+      if ((st = make_tmap_heads(&maps[3 + 2 * s], kk[s], a.dtype, frames, a.L, a.heads, hd, strides[s], BN)) != PAID_OK) return st;
+      if ((st = make_tmap_heads(&maps[4 + 2 * s], vv[s], a.dtype, frames, a.L, a.heads, hd, strides[s], BN)) != PAID_OK) return st;
       ta.per_frame[1 + s] = strides[s] ? 1 : 0;
     } else {  // unused slot: any valid descriptor
       maps[3 + 2 * s] = maps[1];
@@ -449,7 +459,7 @@ int launch_attn_tc(const CoreArgs& a, cudaStream_t stream) {
       ta.per_frame[1 + s] = 1;
     }
   }
-  ta.mode = a.mode; ta.fused = a.fused; ta.N = a.N; ta.S = a.S; ta.L = a.L; ta.heads = a.heads;
+  ta.mode = a.mode; ta.fused = a.fused; ta.N = a.N; ta.S = a.S; ta.L = a.L; ta.heads = a.heads; ta.head_dim = hd;
   ta.begin_frame = a.begin_frame; ta.end_frame = a.end_frame;
   ta.scale_log2 = a.scale * kLog2e;
   ta.coef = a.coef; ta.out = a.out;

@@ -135,9 +135,15 @@ static int core_dispatch(const CoreArgs& a, uint32_t flags, cudaStream_t stream)
   ProfileState& ps = prof();
   const size_t before = ps.on ? ps.used.size() : 0;
   int st;
-  if (!(flags & PAID_FLAG_GENERIC_KERNELS) && attn_tc_supported(a)) {
-    *last_kernel_slot() = "tcgen05";
+  static std::atomic<bool> pad_rejected{false};  // zero-padded head_dim < 64 needs a box wider than the tensor
+  if (!(flags & PAID_FLAG_GENERIC_KERNELS) && attn_tc_supported(a) && !(a.head_dim < 64 && pad_rejected.load())) {
+    *last_kernel_slot() = a.head_dim < 64 ? "tcgen05-padded" : "tcgen05";
     st = launch_attn_tc(a, stream);
+    if (st == PAID_EUNSUPPORTED && a.head_dim < 64) {  // descriptor refused before any launch: other CUDA kernel family
+      pad_rejected.store(true);
+      *last_kernel_slot() = "generic";
+      st = launch_attn_generic(a, stream);
+    }
   } else {
     *last_kernel_slot() = "generic";
     st = launch_attn_generic(a, stream);

@@ -96,6 +96,28 @@ def test_sdxl_geometry_against_oracle(cabi, m, fused):
 
 
 @pytest.mark.parametrize("m,fused", MODES)
+def test_sd15_geometry_padded_head_dim(cabi, m, fused):
+    """SD1.5 64x64 level (C=320, 8 heads of 40; S reduced to 1024 so the oracle finishes in seconds), self and cross:
+    head_dim 40 runs on the tcgen05 kernel zero-padded to 64 by the TMA unit; it must agree with the oracle and
+    with the generic CUDA kernel, and bf16 must stay inside its gate."""
+    mode = O.MODE_NAMES[m]
+    for L in (None, 77):
+        w = O.make_layer(320, 320 if L is None else 768, 8, 51)
+        x, ctx = O.make_inputs(5, 1024, 320, L, 768, 51)
+        coef = O.coefficients(5, 4, 4)
+        y = run_layer(cabi, w, x, ctx, coef, mode, fused)
+        kernel = cabi.last_kernel()
+        assert kernel in ("tcgen05-padded", "generic"), kernel   # generic only if the driver refuses the padded box
+        wr = O.LayerWeights(*(rounded(t) for t in (w.wq, w.wk, w.wv, w.wo, w.bo)), heads=8)
+        ref = O.forward_chunked(rounded(x), rounded(ctx), wr, coef, mode, fused, rows=256)
+        check(y, ref, (m, fused, L, kernel), rel=1e-3)
+        yg = run_layer(cabi, w, x, ctx, coef, mode, fused, flags=cabi.FLAG_GENERIC_KERNELS)
+        check(y, yg, (m, fused, L, "padded tcgen05 == generic"), rel=1e-3)
+        yb = run_layer(cabi, w, x, ctx, coef, mode, fused, dtype=torch.bfloat16)
+        check(yb, ref, (m, fused, L, "bf16"), rel=8 * REL, maxabs=8 * MAXABS)
+
+
+@pytest.mark.parametrize("m,fused", MODES)
 def test_properties_at_full_size(cabi, m, fused):
     """Size-independent properties at BASELINE config sizes (SDXL 64x64 level: S=4096, C=640, 10 heads; N=7):
     endpoint frames equal plain attention; the N-frame batch equals 3-frame [0, i, N-1] batches; a frame-sharded
@@ -145,7 +167,8 @@ def test_linear_against_torch(cabi, pairs, monkeypatch):
 
 def test_core_edge_shapes(cabi):
     """Ragged sizes: S and L not multiples of any tile, L smaller than a tile, single query row."""
-    for S, L, h, d in ((1, 1, 1, 64), (130, 77, 2, 64), (257, 300, 1, 64), (64, 5, 3, 40), (33, 129, 1, 160)):
+    for S, L, h, d in ((1, 1, 1, 64), (130, 77, 2, 64), (257, 300, 1, 64), (64, 5, 3, 40), (33, 129, 1, 160),
+                       (300, 130, 3, 40), (129, 65, 5, 16), (200, 77, 2, 56), (70, 70, 2, 80)):
         N, Cd = 3, h * d
         torch.manual_seed(S + L)
         q, k, v = (torch.randn(N, T, Cd) for T in (S, L, L))
