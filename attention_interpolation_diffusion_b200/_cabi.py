@@ -26,7 +26,7 @@ EXPORTS = [
     "paid_attn_abi_version", "paid_attn_workspace_bytes", "paid_attn_core_workspace_bytes", "paid_attn_forward",
     "paid_attn_core", "paid_attn_project_endpoints", "paid_linear", "paid_attn_last_error",
     "paid_attn_launch_count", "paid_attn_last_kernel", "paid_attn_profile_enable", "paid_attn_profile_read",
-    "paid_geglu",
+    "paid_geglu", "paid_add_layer_norm", "paid_group_norm_nhwc", "paid_group_norm_workspace_bytes",
 ]
 
 
@@ -85,6 +85,13 @@ def load_library() -> C.CDLL:
                                 C.c_int32, C.c_uint32, C.c_void_p]
     lib.paid_geglu.restype = C.c_int
     lib.paid_geglu.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    lib.paid_add_layer_norm.restype = C.c_int
+    lib.paid_add_layer_norm.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_void_p]
+    lib.paid_group_norm_workspace_bytes.restype = C.c_uint64
+    lib.paid_group_norm_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32]
+    lib.paid_group_norm_nhwc.restype = C.c_int
+    lib.paid_group_norm_nhwc.argtypes = [C.c_void_p] * 6 + [C.c_uint64, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_float,
+                                         C.c_int32, C.c_int32, C.c_void_p]
     lib.paid_attn_last_error.restype = C.c_char_p
     lib.paid_attn_launch_count.restype = C.c_uint64
     lib.paid_attn_last_kernel.restype = C.c_char_p
@@ -233,6 +240,47 @@ def geglu(h: torch.Tensor) -> torch.Tensor:
     out = torch.empty(*h.shape[:-1], D, dtype=h.dtype, device=h.device)
     _check(lib.paid_geglu(h.data_ptr(), out.data_ptr(), h.numel() // (2 * D), D, _dtype_code(h), _stream(h)), "paid_geglu")
     return out
+
+
+def add_layer_norm(x: torch.Tensor, delta: Optional[torch.Tensor], weight: torch.Tensor, bias: torch.Tensor,
+                   eps: float = 1e-5):
+    """``paid_add_layer_norm``: returns (x + delta, LayerNorm(x + delta) * weight + bias) over the last dim; with
+    ``delta=None`` the first element is ``x`` itself.  x, delta: (..., C) contiguous."""
+    lib = load_library()
+    _dev_check(x, delta, weight, bias)
+    Cdim = x.shape[-1]
+    if not x.is_contiguous() or (delta is not None and (not delta.is_contiguous() or delta.shape != x.shape)):
+        raise ValueError("add_layer_norm: x and delta must be contiguous and of the same shape")
+    h = torch.empty_like(x)
+    x_out = torch.empty_like(x) if delta is not None else x
+    _check(lib.paid_add_layer_norm(x.data_ptr(), None if delta is None else delta.data_ptr(), weight.data_ptr(),
+                                   bias.data_ptr(), None if delta is None else x_out.data_ptr(), h.data_ptr(),
+                                   x.numel() // Cdim, Cdim, float(eps), _dtype_code(x), _stream(x)), "paid_add_layer_norm")
+    return x_out, h
+
+
+def group_norm_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, groups: int, eps: float = 1e-5,
+                    silu: bool = False, pre_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``paid_group_norm_nhwc`` on a channels-last (N, C, H, W) feature map; returns a channels-last tensor of the same
+    logical shape.  ``pre_bias`` (N, C) is added to x before the statistics (the ResNet time-embedding add)."""
+    lib = load_library()
+    _dev_check(weight, bias, pre_bias)
+    if not x.is_cuda:
+        raise RuntimeError("libpaid_attn needs CUDA tensors; there is no CPU path")
+    if x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("group_norm_nhwc: x must be a 4-D channels_last tensor")
+    N, Cdim, H, W = x.shape
+    if pre_bias is not None and (pre_bias.shape != (N, Cdim) or not pre_bias.is_contiguous()):
+        raise ValueError("group_norm_nhwc: pre_bias must be a contiguous (N, C) tensor")
+    need = int(lib.paid_group_norm_workspace_bytes(N, H * W, Cdim, groups))
+    if need == 0:
+        raise RuntimeError(f"paid_group_norm_nhwc: unsupported geometry C={Cdim} groups={groups}")
+    ws = _workspace(x.device, need)          # the per-device scratch shared (stream-ordered) with the attention calls
+    y = torch.empty_like(x, memory_format=torch.channels_last)
+    _check(lib.paid_group_norm_nhwc(x.data_ptr(), None if pre_bias is None else pre_bias.data_ptr(), weight.data_ptr(),
+                                    bias.data_ptr(), y.data_ptr(), ws.data_ptr(), ws.numel(), N, H * W, Cdim, groups,
+                                    float(eps), int(bool(silu)), _dtype_code(x), _stream(x)), "paid_group_norm_nhwc")
+    return y
 
 
 def attn_core(q, k, v, coef, heads: int, mode: int, fused: bool, scale=None, begin_frame=None, end_frame=None,

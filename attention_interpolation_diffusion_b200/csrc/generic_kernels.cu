@@ -108,6 +108,21 @@ int launch_lerp_endpoints(const void* kb, const void* vb, const void* ke, const 
 // GEGLU: out[m, j] = h[m, j] * gelu(h[m, D + j]), exact erf GELU.  HBM-bound: 16-byte loads / stores,
 // 6 bytes of traffic per output element.
 // ------------------------------------------------------------------------------------------------
+// exact-form GELU 0.5 g (1 + erf(g / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the
+// 16-bit output rounding): one MUFU.RCP, one MUFU.EX2 and 7 FMA-pipe instructions instead of erff's ~30.
+__device__ __forceinline__ float gelu_erf(float g) {
+  const float z = fabsf(g) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erfc_z = p * t * exp2f(-z * z * 1.4426950408889634f);   // 1 - erf(|g| / sqrt 2)
+  const float half_g = 0.5f * g;
+  // g >= 0: 0.5 g (2 - erfc) ;  g < 0: 0.5 g erfc
+  return g >= 0.f ? fmaf(-half_g, erfc_z, g) : half_g * erfc_z;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) geglu_kernel(const T* __restrict__ h, T* __restrict__ out, long long M, int D) {
   const int vec_per_row = D / 8;
@@ -123,8 +138,8 @@ __global__ void __launch_bounds__(256) geglu_kernel(const T* __restrict__ h, T* 
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float g0 = to_f32(g8[2 * e]), g1 = to_f32(g8[2 * e + 1]);
-      const float r0 = to_f32(a8[2 * e]) * (0.5f * g0 * (1.f + erff(g0 * 0.70710678118654752f)));
-      const float r1 = to_f32(a8[2 * e + 1]) * (0.5f * g1 * (1.f + erff(g1 * 0.70710678118654752f)));
+      const float r0 = to_f32(a8[2 * e]) * gelu_erf(g0);
+      const float r1 = to_f32(a8[2 * e + 1]) * gelu_erf(g1);
       o[e] = pack2<T>(r0, r1);
     }
     *reinterpret_cast<uint4*>(out + m * D + j) = make_uint4(o[0], o[1], o[2], o[3]);

@@ -249,6 +249,41 @@ int paid_geglu(const void* h, void* out, int64_t M, int32_t D, int32_t dtype, vo
   return launch_geglu(h, out, M, D, dtype, (cudaStream_t)cuda_stream);
 }
 
+int paid_add_layer_norm(const void* x, const void* delta, const void* gamma, const void* beta, void* x_out, void* h_out,
+                        int64_t rows, int32_t C, float eps, int32_t dtype, void* cuda_stream) {
+  if (!x || !gamma || !beta || !h_out) return fail(PAID_EINVAL, "paid_add_layer_norm: x, gamma, beta, h_out must be non-NULL");
+  if (delta && !x_out) return fail(PAID_EINVAL, "paid_add_layer_norm: x_out must be given with delta");
+  if (rows <= 0 || C <= 0) return fail(PAID_EINVAL, "paid_add_layer_norm: sizes must be positive");
+  if (dtype != PAID_F16 && dtype != PAID_BF16) return fail(PAID_EINVAL, "paid_add_layer_norm: bad dtype");
+  if (!add_layer_norm_supported(C)) return fail(PAID_EUNSUPPORTED, "paid_add_layer_norm: C=%d must be a multiple of 8, <= 2048", C);
+  if (((uintptr_t)x | (uintptr_t)delta | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)x_out | (uintptr_t)h_out) & 15)
+    return fail(PAID_EINVAL, "paid_add_layer_norm: pointers must be 16-byte aligned");
+  return launch_add_layer_norm(x, delta, gamma, beta, x_out, h_out, rows, C, eps, dtype, (cudaStream_t)cuda_stream);
+}
+
+uint64_t paid_group_norm_workspace_bytes(int32_t N, int64_t HW, int32_t C, int32_t groups) {
+  if (!group_norm_supported(C, groups)) return 0;
+  return group_norm_workspace_bytes(N, HW, C, groups);
+}
+
+int paid_group_norm_nhwc(const void* x, const void* pre_bias, const void* gamma, const void* beta, void* y, void* workspace,
+                         uint64_t workspace_bytes, int32_t N, int64_t HW, int32_t C, int32_t groups, float eps,
+                         int32_t silu, int32_t dtype, void* cuda_stream) {
+  if (!x || !gamma || !beta || !y) return fail(PAID_EINVAL, "paid_group_norm_nhwc: x, gamma, beta, y must be non-NULL");
+  if (N <= 0 || N > 65535 || HW <= 0 || C <= 0 || groups <= 0) return fail(PAID_EINVAL, "paid_group_norm_nhwc: bad sizes");
+  if (dtype != PAID_F16 && dtype != PAID_BF16) return fail(PAID_EINVAL, "paid_group_norm_nhwc: bad dtype");
+  if (!group_norm_supported(C, groups))
+    return fail(PAID_EUNSUPPORTED, "paid_group_norm_nhwc: C=%d groups=%d (need C %% 8 == 0, C <= 4096, groups <= 64, C %% groups == 0)", C, groups);
+  if (((uintptr_t)x | (uintptr_t)pre_bias | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)y | (uintptr_t)workspace) & 15)
+    return fail(PAID_EINVAL, "paid_group_norm_nhwc: pointers must be 16-byte aligned");
+  const uint64_t need = group_norm_workspace_bytes(N, HW, C, groups);
+  if (!workspace || workspace_bytes < need)
+    return fail(PAID_EWORKSPACE, "paid_group_norm_nhwc: workspace needs %llu bytes, got %llu", (unsigned long long)need,
+                (unsigned long long)workspace_bytes);
+  return launch_group_norm_nhwc(x, pre_bias, gamma, beta, y, (float*)workspace, N, HW, C, groups, eps, silu ? 1 : 0, dtype,
+                                (cudaStream_t)cuda_stream);
+}
+
 int paid_attn_core(const PaidCoreParams* p, void* cuda_stream) {
   if (!p) return fail(PAID_EINVAL, "params is NULL");
   if (p->struct_size != sizeof(PaidCoreParams))

@@ -151,6 +151,13 @@ int launch_attn_generic(const CoreArgs& a, cudaStream_t stream);
 int launch_attn_tc(const CoreArgs& a, cudaStream_t stream);
 bool attn_tc_supported(const CoreArgs& a);
 int launch_geglu(const void* h, void* out, long long M, int D, int dtype, cudaStream_t stream);
+int launch_add_layer_norm(const void* x, const void* delta, const void* gamma, const void* beta, void* x_out, void* h_out,
+                          long long rows, int C, float eps, int dtype, cudaStream_t stream);
+bool add_layer_norm_supported(int C);
+int launch_group_norm_nhwc(const void* x, const void* pre_bias, const void* gamma, const void* beta, void* y, float* ws, int N,
+                           long long HW, int C, int groups, float eps, int silu, int dtype, cudaStream_t stream);
+unsigned long long group_norm_workspace_bytes(int N, long long HW, int C, int groups);
+bool group_norm_supported(int C, int groups);
 int launch_lerp_endpoints(const void* kb, const void* vb, const void* ke, const void* ve, const float* coef,
                           void* kx, void* vx, int N, long long LC, int dtype, cudaStream_t stream);
 

@@ -13,6 +13,7 @@ diffusers, so the processors of ``interpolation.py`` install with ``set_attn_pro
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -58,6 +59,42 @@ def sinusoidal(t: torch.Tensor, dim: int) -> torch.Tensor:
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
 
+# tests (and PAID_NATIVE_GLUE=0 for A/B timing) flip this to compare the fused glue kernels with the PyTorch composition
+NATIVE_GLUE = os.environ.get("PAID_NATIVE_GLUE", "1") != "0"
+
+
+def _native(x: torch.Tensor) -> bool:
+    """Half-precision CUDA tensors take libpaid_attn's fused glue kernels; anything else (the CPU tests that host the
+    oracle processors in this harness) takes the plain PyTorch composition of the same ops."""
+    return NATIVE_GLUE and x.is_cuda and x.dtype in (torch.float16, torch.bfloat16)
+
+
+def group_norm(gn: nn.GroupNorm, x: torch.Tensor, silu: bool = False, pre_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """act(GroupNorm(x + pre_bias[:, :, None, None])): one statistics pass + one normalise/SiLU pass over the
+    channels-last tensor (``paid_group_norm_nhwc``) instead of PyTorch's NHWC->NCHW copy, moments, normalise, SiLU and
+    NCHW->NHWC copy kernels."""
+    if _native(x):
+        from . import _cabi
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        return _cabi.group_norm_nhwc(x, gn.weight, gn.bias, gn.num_groups, gn.eps, silu, pre_bias)
+    if pre_bias is not None:
+        x = x + pre_bias[:, :, None, None]
+    h = gn(x)
+    return F.silu(h) if silu else h
+
+
+def add_layer_norm(ln: nn.LayerNorm, x: torch.Tensor, delta: Optional[torch.Tensor]):
+    """(x + delta, LayerNorm(x + delta)): the residual add of the previous sub-layer fused with the norm in front of
+    the next one (``paid_add_layer_norm``, one pass over the row)."""
+    if _native(x):
+        from . import _cabi
+        return _cabi.add_layer_norm(x, delta, ln.weight, ln.bias, ln.eps)
+    if delta is not None:
+        x = x + delta
+    return x, ln(x)
+
+
 class ResnetBlock2D(nn.Module):
     def __init__(self, cin, cout, temb_ch):
         super().__init__()
@@ -69,9 +106,9 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, temb):
-        h = self.conv1(F.silu(self.norm1(x)))
-        h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
-        h = self.conv2(F.silu(self.norm2(h)))
+        h = self.conv1(group_norm(self.norm1, x, silu=True))
+        # h + time_emb[:, :, None, None] is folded into the load of the second norm
+        h = self.conv2(group_norm(self.norm2, h, silu=True, pre_bias=self.time_emb_proj(F.silu(temb))))
         return (x if self.conv_shortcut is None else self.conv_shortcut(x)) + h
 
 
@@ -100,10 +137,14 @@ class BasicTransformerBlock(nn.Module):
         self.norm3 = nn.LayerNorm(dim)
         self.ff = FeedForward(dim)
 
-    def forward(self, x, ctx):
-        x = x + self.attn1(self.norm1(x))
-        x = x + self.attn2(self.norm2(x), encoder_hidden_states=ctx)
-        return x + self.ff(self.norm3(x))
+    def forward(self, x, ctx, pending=None):
+        """x = x + attn1(norm1(x)); x = x + attn2(norm2(x), ctx); x = x + ff(norm3(x)), with every residual add fused
+        into the LayerNorm that follows it.  ``pending`` is the previous block's feed-forward output, not yet added to
+        x; returns (x, pending) in the same form."""
+        x, h = add_layer_norm(self.norm1, x, pending)
+        x, h = add_layer_norm(self.norm2, x, self.attn1(h))
+        x, h = add_layer_norm(self.norm3, x, self.attn2(h, encoder_hidden_states=ctx))
+        return x, self.ff(h)
 
 
 class Transformer2DModel(nn.Module):
@@ -118,14 +159,16 @@ class Transformer2DModel(nn.Module):
     def forward(self, x, ctx):
         b, c, hh, ww = x.shape
         res = x
-        h = self.norm(x)
+        h = group_norm(self.norm, x)
         if self.linear_proj:
             h = self.proj_in(h.permute(0, 2, 3, 1).reshape(b, hh * ww, c))
         else:
             h = self.proj_in(h).permute(0, 2, 3, 1).reshape(b, hh * ww, c)
         h = h.contiguous()
+        pending = None
         for blk in self.transformer_blocks:
-            h = blk(h, ctx)
+            h, pending = blk(h, ctx, pending)
+        h = h + pending
         if self.linear_proj:
             h = self.proj_out(h).reshape(b, hh, ww, c).permute(0, 3, 1, 2)
         else:
@@ -278,7 +321,7 @@ class UNetHarness(nn.Module):
         x = self.mid_block(x, temb, encoder_hidden_states)
         for blk in self.up_blocks:
             x = blk(x, skips, temb, encoder_hidden_states)
-        return self.conv_out(F.silu(self.conv_norm_out(x)))
+        return self.conv_out(group_norm(self.conv_norm_out, x, silu=True))
 
 
 def build_unet(name: str, device="cuda", dtype=torch.float16, seed: int = 1002) -> UNetHarness:

@@ -134,6 +134,27 @@ def kernel_rooflines(net, frames, atype, peak_tf):
     return out
 
 
+def attention_traffic(net, frames, n_aid, n_plain):
+    """roofline.traffic: ncu DRAM bytes (read + write) per attention-core launch, averaged over the launch mix of one
+    sequence, from the committed `ncu --set full` capture (profiles/attn_traffic.json: one row per SDXL attention-layer
+    class and mode at 7 frames; scaled linearly with the frame count).  None if no capture covers the geometry."""
+    p = os.path.join(ROOT, "profiles", "attn_traffic.json")
+    if not os.path.exists(p):
+        return None, None, "no ncu capture committed"
+    rows = {(r["S"], r["L"], r["heads"], r["mode"]): r for r in json.load(open(p))["rows"]}
+    total = launches = alg = 0.0
+    for g in net.attention_geometry():
+        for mode, reps in (("interpolated", n_aid), ("plain", n_plain)):
+            r = rows.get((g["S"], g["L"], g["heads"], mode))
+            if r is None:
+                return None, None, "ncu capture does not cover this geometry"
+            total += reps * (r["dram_read_bytes"] + r["dram_write_bytes"]) * frames / r["frames"]
+            alg += reps * 2.0 * (2 * frames * g["S"] * g["C"] + 2 * frames * g["L"] * g["C"])   # Q, K, V read + H written
+            launches += reps
+    return total / launches, alg / launches, (f"launch-weighted mean over {int(launches)} launches of one sequence; per-shape rows in "
+                              "profiles/attn_traffic.json (ncu --set full, tools/ncu_core.py)")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -312,13 +333,15 @@ def run_own_arm(args):
         peak_tf, _, peak_src = peaks()
         achieved = k_flops / (k_ms / 1000.0) / 1e12 if k_ms > 0 else None
         by_shape = kernel_rooflines(net, frames // world, args.atype, peak_tf)
+        n_aid = int(args.denoise_steps * WARMUP_RATIO)
+        traffic, alg_bytes, traffic_how = attention_traffic(net, frames // world, n_aid, 2 * args.denoise_steps - n_aid)
         roofline = {"kernel": f"attention core ({_cabi.last_kernel()})", "bound": "tensor", "achieved": achieved,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None,
-                    "peak_source": peak_src, "traffic": None, "launches": k_launches,
+                    "peak_source": peak_src, "traffic": traffic, "traffic_unit": "bytes per launch",
+                    "traffic_how": traffic_how, "launches": k_launches,
                     "avg_launch_ms": k_ms / max(k_launches, 1), "share_of_step": k_ms / (ms / args.steps),
                     "eager_step_ms": ms_eager, "by_shape_isolated": by_shape,
-                    "traffic_note": "ncu dram bytes per launch, dominant shape (S=L=4096, C=640, fused-outer, N=7): "
-                                    "118 MB read + 29 MB write vs 110 + 37 MB algorithmic (profiles/r1_ncu_attn_v4.txt)",
+                    "algorithmic_bytes_per_launch": alg_bytes,
                     "how": "CUDA events around every attention-core launch of one extra, eagerly launched sequence "
                            "after the timed region (the timed steps replay CUDA graphs); share_of_step = summed "
                            "kernel time / timed step; algorithmic flops per SURVEY.md 8d (fused-outer 6A, "

@@ -141,6 +141,24 @@ int paid_linear(const void* x, const void* w, const void* bias, void* y, int64_t
  * h is (M, 2*D) = [a | g] per row (output of the first FF Linear), out (M, D) = a * gelu(g), exact (erf) GELU. */
 int paid_geglu(const void* h, void* out, int64_t M, int32_t D, int32_t dtype, void* cuda_stream);
 
+/* Residual add + LayerNorm in front of every attention / feed-forward call of the transformer block (the caller of
+ * the path; diffusers BasicTransformerBlock: x = x + attn(norm(x)) ...):
+ *   x_out (rows,C) = x + delta          (skipped when delta is NULL; x_out may alias x or delta)
+ *   h_out (rows,C) = LayerNorm(x_out) * gamma + beta     (statistics in fp32 over the C channels of a row)
+ * C must be a multiple of 8 and at most 2048. */
+int paid_add_layer_norm(const void* x, const void* delta, const void* gamma, const void* beta, void* x_out, void* h_out,
+                        int64_t rows, int32_t C, float eps, int32_t dtype, void* cuda_stream);
+
+/* GroupNorm (+ optional SiLU) of a channels-last feature map: x, y are (N, HW, C) = NHWC, gamma / beta (C,);
+ * statistics per (frame, group) over HW x (C / groups) elements in fp32, fixed reduction order.
+ * pre_bias: NULL or (N, C), added to x on load (the ResNet block's time-embedding add in front of its second norm).
+ * workspace: >= paid_group_norm_workspace_bytes(...) bytes of caller-owned scratch for the partial statistics.
+ * C % 8 == 0, C <= 4096, groups <= 64, C % groups == 0. */
+uint64_t paid_group_norm_workspace_bytes(int32_t N, int64_t HW, int32_t C, int32_t groups);
+int paid_group_norm_nhwc(const void* x, const void* pre_bias, const void* gamma, const void* beta, void* y, void* workspace,
+                         uint64_t workspace_bytes, int32_t N, int64_t HW, int32_t C, int32_t groups, float eps,
+                         int32_t silu, int32_t dtype, void* cuda_stream);
+
 /* message for the last non-OK status returned on this thread ("" if none) */
 const char* paid_attn_last_error(void);
 
@@ -148,7 +166,7 @@ const char* paid_attn_last_error(void);
 uint64_t paid_attn_launch_count(void);
 
 /* name of the attention kernel family the last paid_attn_core / paid_attn_forward call on this thread used:
- * "tcgen05" or "generic" ("" before the first call) */
+ * "tcgen05", "tcgen05-padded" (head_dim < 64 zero-padded to 64 by the TMA unit) or "generic" ("" before the first call) */
 const char* paid_attn_last_kernel(void);
 
 /* Measurement hook (bench.py roofline): while enabled, every attention-core kernel launched by

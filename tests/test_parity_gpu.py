@@ -390,3 +390,81 @@ def test_geglu_against_torch(cabi):
         ref = h[:, :D].float() * torch.nn.functional.gelu(h[:, D:].float())
         out = cabi.geglu(h).float()
         check(out.cpu(), ref.cpu(), ("geglu", M, D, dt), rel=1e-3 if dt == torch.float16 else 8e-3, maxabs=4e-2)
+
+
+def test_add_layer_norm_against_torch(cabi):
+    """paid_add_layer_norm vs torch in fp32: the residual sum is bit-exact (fp32 add, one rounding), the norm is
+    within fp16 rounding of F.layer_norm on that sum; rows / widths of every SD1.5 / SDXL transformer level + ragged."""
+    torch.manual_seed(4)
+    F = torch.nn.functional
+    for rows, C, dt in ((7 * 1024, 1280, torch.float16), (2 * 4096, 640, torch.float16), (333, 320, torch.float16),
+                        (5, 2048, torch.float16), (64, 8, torch.float16), (1000, 1280, torch.bfloat16)):
+        x = (torch.randn(rows, C, device="cuda") * 3 + 0.5).to(dt)
+        d = torch.randn(rows, C, device="cuda").to(dt)
+        g = (1 + 0.1 * torch.randn(C, device="cuda")).to(dt)
+        b = (0.1 * torch.randn(C, device="cuda")).to(dt)
+        tol = dict(rel=1e-3, maxabs=2e-2) if dt == torch.float16 else dict(rel=8e-3, maxabs=8e-2)
+        x0, h0 = cabi.add_layer_norm(x, None, g, b, 1e-5)
+        assert x0 is x
+        check(h0.float().cpu(), F.layer_norm(x.float(), (C,), g.float(), b.float(), 1e-5).cpu(), ("ln", rows, C, dt), **tol)
+        x1, h1 = cabi.add_layer_norm(x, d, g, b, 1e-5)
+        assert torch.equal(x1, x + d), ("residual sum", rows, C, dt)
+        check(h1.float().cpu(), F.layer_norm(x1.float(), (C,), g.float(), b.float(), 1e-5).cpu(), ("add+ln", rows, C, dt), **tol)
+        x2, h2 = cabi.add_layer_norm(x, d, g, b, 1e-5)
+        assert torch.equal(h1, h2) and torch.equal(x1, x2)
+
+
+def test_group_norm_nhwc_against_torch(cabi):
+    """paid_group_norm_nhwc (+ SiLU, + per-(n,c) pre-bias) vs torch GroupNorm in fp32 on every channel width the
+    SD1.5 / SDXL UNets normalise (incl. the skip concatenations), odd spatial sizes, a large mean offset (variance by
+    partial (mean, M2) merging, not E[x^2] - E[x]^2 over the whole group), and bit-exact repeatability."""
+    torch.manual_seed(6)
+    F = torch.nn.functional
+    shapes = [(7, 320, 128, 128), (3, 640, 64, 64), (2, 960, 32, 32), (2, 1280, 32, 32), (1, 1920, 16, 16), (2, 2560, 8, 8),
+              (2, 128, 16, 16), (2, 384, 8, 8), (3, 64, 1, 1), (2, 320, 7, 9), (1, 256, 33, 5)]
+    for (N, C, H, W) in shapes:
+        for dt in (torch.float16, torch.bfloat16):
+            x = (torch.randn(N, C, H, W, device="cuda") * 2 + 3).to(dt).contiguous(memory_format=torch.channels_last)
+            g = (1 + 0.1 * torch.randn(C, device="cuda")).to(dt)
+            b = (0.1 * torch.randn(C, device="cuda")).to(dt)
+            pb = torch.randn(N, C, device="cuda").to(dt)
+            tol = dict(rel=1e-3, maxabs=2e-2) if dt == torch.float16 else dict(rel=8e-3, maxabs=8e-2)
+            for silu in (False, True):
+                for pre in (None, pb):
+                    y = cabi.group_norm_nhwc(x, g, b, 32, 1e-5, silu, pre)
+                    assert y.shape == x.shape and y.is_contiguous(memory_format=torch.channels_last)
+                    xin = x if pre is None else x + pre[:, :, None, None]
+                    ref = F.group_norm(xin.float(), 32, g.float(), b.float(), 1e-5)
+                    ref = F.silu(ref) if silu else ref
+                    check(y.float().cpu(), ref.cpu(), ("gn", N, C, H, W, dt, silu, pre is not None), **tol)
+                    assert torch.equal(y, cabi.group_norm_nhwc(x, g, b, 32, 1e-5, silu, pre))
+    with pytest.raises(ValueError):
+        cabi.group_norm_nhwc(torch.zeros(2, 64, 4, 4, device="cuda").half(), g[:64], b[:64], 32)   # not channels_last
+    with pytest.raises(RuntimeError):
+        z = torch.zeros(2, 100, 4, 4, device="cuda").half().contiguous(memory_format=torch.channels_last)
+        cabi.group_norm_nhwc(z, g[:100], b[:100], 25)                                                # C % 8 != 0
+
+
+def test_unet_forward_native_glue_equals_torch_glue(cabi):
+    """The harness with the fused GroupNorm / add+LayerNorm kernels against the same harness on PyTorch's
+    group_norm / layer_norm / add kernels (tiny UNet, AID on and off)."""
+    from attention_interpolation_diffusion_b200 import unet_harness as U
+    from attention_interpolation_diffusion_b200.pipeline import InterpolationPipeline
+    net = U.build_unet("tiny", "cuda", torch.float16, seed=3)
+    pipe = InterpolationPipeline(net, use_cuda_graphs=False)
+    pipe.load_aid(t=None, is_fused=True, atype="fused_outer", size=4, alpha=2, beta=2)
+    g = torch.Generator("cpu").manual_seed(1)
+    lat = torch.randn(4, 4, 16, 16, generator=g).cuda().half().contiguous(memory_format=torch.channels_last)
+    ctx = torch.randn(4, 77, 96, generator=g).cuda().half()
+    added = {"text_embeds": torch.randn(4, 1280, generator=g).cuda().half(), "time_ids": torch.zeros(4, 6).cuda().half()}
+    outs = {}
+    for aid in (True, False):
+        pipe.set_coefs(torch.linspace(0, 1, 4)) if aid else pipe.deactivate_aid()
+        for native in (True, False):
+            U.NATIVE_GLUE = native
+            try:
+                with torch.no_grad():
+                    outs[(aid, native)] = net(lat, 500, ctx, added).float().cpu()
+            finally:
+                U.NATIVE_GLUE = True
+        check(outs[(aid, True)], outs[(aid, False)], ("native glue vs torch glue", aid), rel=5e-3, maxabs=5e-2)
