@@ -27,6 +27,7 @@ EXPORTS = [
     "paid_attn_core", "paid_attn_project_endpoints", "paid_linear", "paid_attn_last_error",
     "paid_attn_launch_count", "paid_attn_last_kernel", "paid_attn_profile_enable", "paid_attn_profile_read",
     "paid_geglu", "paid_add_layer_norm", "paid_group_norm_nhwc", "paid_group_norm_workspace_bytes",
+    "paid_residual_bias_add",
 ]
 
 
@@ -87,6 +88,8 @@ def load_library() -> C.CDLL:
     lib.paid_geglu.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.paid_add_layer_norm.restype = C.c_int
     lib.paid_add_layer_norm.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_void_p]
+    lib.paid_residual_bias_add.restype = C.c_int
+    lib.paid_residual_bias_add.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.paid_group_norm_workspace_bytes.restype = C.c_uint64
     lib.paid_group_norm_workspace_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32]
     lib.paid_group_norm_nhwc.restype = C.c_int
@@ -281,6 +284,20 @@ def group_norm_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, g
                                     bias.data_ptr(), y.data_ptr(), ws.data_ptr(), ws.numel(), N, H * W, Cdim, groups,
                                     float(eps), int(bool(silu)), _dtype_code(x), _stream(x)), "paid_group_norm_nhwc")
     return y
+
+
+def residual_bias_add(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """``paid_residual_bias_add`` on two channels-last (N, C, H, W) feature maps: a + b + bias[None, :, None, None]."""
+    lib = load_library()
+    _dev_check(bias)
+    if a.shape != b.shape or a.dim() != 4 or not a.is_cuda or not b.is_cuda or not (
+            a.is_contiguous(memory_format=torch.channels_last) and b.is_contiguous(memory_format=torch.channels_last)):
+        raise ValueError("residual_bias_add: a and b must be channels_last CUDA tensors of the same 4-D shape")
+    N, Cdim, H, W = a.shape
+    out = torch.empty_like(a, memory_format=torch.channels_last)
+    _check(lib.paid_residual_bias_add(a.data_ptr(), b.data_ptr(), bias.data_ptr(), out.data_ptr(), N * H * W, Cdim,
+                                      _dtype_code(a), _stream(a)), "paid_residual_bias_add")
+    return out
 
 
 def attn_core(q, k, v, coef, heads: int, mode: int, fused: bool, scale=None, begin_frame=None, end_frame=None,

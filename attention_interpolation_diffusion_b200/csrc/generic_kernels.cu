@@ -124,37 +124,54 @@ __device__ __forceinline__ float gelu_erf(float g) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) geglu_kernel(const T* __restrict__ h, T* __restrict__ out, long long M, int D) {
-  const int vec_per_row = D / 8;
-  const long long total = M * vec_per_row;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long m = i / vec_per_row;
-    const int j = (int)(i % vec_per_row) * 8;
-    const uint4 av = *reinterpret_cast<const uint4*>(h + m * 2 * D + j);
-    const uint4 gv = *reinterpret_cast<const uint4*>(h + m * 2 * D + D + j);
-    const T* a8 = reinterpret_cast<const T*>(&av);
-    const T* g8 = reinterpret_cast<const T*>(&gv);
-    uint32_t o[4];
+__global__ void __launch_bounds__(256) geglu_kernel(const T* __restrict__ h, T* __restrict__ out, unsigned total, unsigned vec_per_row) {
+  // 32-bit index arithmetic (the launcher checks M * D / 8 < 2^31): a 64-bit division per vector costs more than the math
+  const unsigned stride = gridDim.x * blockDim.x, D = vec_per_row * 8;
+  for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+    uint4 av[2], gv[2];
+    unsigned m[2], j[2];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float g0 = to_f32(g8[2 * e]), g1 = to_f32(g8[2 * e + 1]);
-      const float r0 = to_f32(a8[2 * e]) * gelu_erf(g0);
-      const float r1 = to_f32(a8[2 * e + 1]) * gelu_erf(g1);
-      o[e] = pack2<T>(r0, r1);
+    for (int u = 0; u < 2; ++u) {
+      const unsigned i = i0 + u * stride;
+      m[u] = i / vec_per_row;
+      j[u] = (i - m[u] * vec_per_row) * 8;
     }
-    *reinterpret_cast<uint4*>(out + m * D + j) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {   // four independent 16-byte loads in flight per thread
+      if (i0 + u * stride < total) {
+        av[u] = *reinterpret_cast<const uint4*>(h + (size_t)m[u] * 2 * D + j[u]);
+        gv[u] = *reinterpret_cast<const uint4*>(h + (size_t)m[u] * 2 * D + D + j[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (i0 + u * stride >= total) break;
+      const T* a8 = reinterpret_cast<const T*>(&av[u]);
+      const T* g8 = reinterpret_cast<const T*>(&gv[u]);
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float g0 = to_f32(g8[2 * e]), g1 = to_f32(g8[2 * e + 1]);
+        const float r0 = to_f32(a8[2 * e]) * gelu_erf(g0);
+        const float r1 = to_f32(a8[2 * e + 1]) * gelu_erf(g1);
+        o[e] = pack2<T>(r0, r1);
+      }
+      *reinterpret_cast<uint4*>(out + (size_t)m[u] * D + j[u]) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
 int launch_geglu(const void* h, void* out, long long M, int D, int dtype, cudaStream_t stream) {
-  long long total = M * (D / 8);
-  long long blocks = (total + 255) / 256;
+  const long long total = M * (D / 8);
+  if (total >= (1LL << 31) - (148LL * 16 * 256 * 2)) return fail(PAID_EUNSUPPORTED, "paid_geglu: M * D / 8 must be below 2^31");
+  long long blocks = (total + 511) / 512;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   if (dtype == PAID_F16)
-    geglu_kernel<__half><<<(unsigned)blocks, 256, 0, stream>>>((const __half*)h, (__half*)out, M, D);
+    geglu_kernel<__half><<<(unsigned)blocks, 256, 0, stream>>>((const __half*)h, (__half*)out, (unsigned)total, (unsigned)(D / 8));
   else
-    geglu_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)h, (__nv_bfloat16*)out, M, D);
+    geglu_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)h, (__nv_bfloat16*)out,
+                                                                      (unsigned)total, (unsigned)(D / 8));
   PAID_LAUNCH_CHECK("geglu_kernel");
   return PAID_OK;
 }

@@ -30,58 +30,107 @@ template <typename T>
 __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack2<T>(f[0], f[1]), pack2<T>(f[2], f[3]), pack2<T>(f[4], f[5]), pack2<T>(f[6], f[7]));
 }
+// one 16-byte read-only load (a dereferenced uint4 temporary handed to unpack8 decays into eight 2-byte loads)
+template <typename T>
+__device__ __forceinline__ uint4 ldg16(const T* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-template <typename T>
+// NV = 16-byte vectors per lane (rows of up to 256 NV channels).  All loads of a row are issued before the first
+// store: x_out may alias x or delta, so the compiler must not be asked to move loads across stores.
+template <typename T, int NV>
 __global__ void __launch_bounds__(kLnWarps * 32)
 add_layer_norm_kernel(const T* x, const T* delta, const T* __restrict__ gamma, const T* __restrict__ beta, T* x_out,
-                      T* __restrict__ h_out, long long rows, int C, float eps) {   // x_out may alias x or delta
+                      T* __restrict__ h_out, long long rows, int C, float eps) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nvec = C >> 3;
   const T* xr = x + row * C;
-  float v[kLnMaxVec][8];
+  uint4 xraw[NV], draw[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = lane + 32 * i;
+    xraw[i] = j < nvec ? *reinterpret_cast<const uint4*>(xr + j * 8) : make_uint4(0, 0, 0, 0);
+  }
+  if (delta) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = lane + 32 * i;
+      draw[i] = j < nvec ? *reinterpret_cast<const uint4*>(delta + row * C + j * 8) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  float v[NV][8];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int j = lane + 32 * i;
-    if (j < nvec) {
-      unpack8<T>(*reinterpret_cast<const uint4*>(xr + j * 8), v[i]);
-      if (delta) {
-        float d[8];
-        unpack8<T>(*reinterpret_cast<const uint4*>(delta + row * C + j * 8), d);
+    unpack8<T>(xraw[i], v[i]);
+    if (delta) {
+      float d[8];
+      unpack8<T>(draw[i], d);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[i][e] = to_f32(from_f32<T>(v[i][e] + d[e]));  // the residual stream is stored in T
-        *reinterpret_cast<uint4*>(x_out + row * C + j * 8) = pack8<T>(v[i]);
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) sum += v[i][e];
+      for (int e = 0; e < 8; ++e) v[i][e] = to_f32(from_f32<T>(v[i][e] + d[e]));  // the residual stream is stored in T
+      if (j < nvec) *reinterpret_cast<uint4*>(x_out + row * C + j * 8) = pack8<T>(v[i]);
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum += v[i][e];   // vectors beyond the row are zero
   }
   const float mean = warp_sum(sum) / (float)C;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i)
+  for (int i = 0; i < NV; ++i)
     if (lane + 32 * i < nvec) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) { const float c = v[i][e] - mean; sq += c * c; }
     }
   const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int j = lane + 32 * i;
     if (j < nvec) {
       float g[8], b[8], o[8];
-      unpack8<T>(*reinterpret_cast<const uint4*>(gamma + j * 8), g);
-      unpack8<T>(*reinterpret_cast<const uint4*>(beta + j * 8), b);
+      unpack8<T>(ldg16(gamma + j * 8), g);
+      unpack8<T>(ldg16(beta + j * 8), b);
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * g[e] + b[e];
       *reinterpret_cast<uint4*>(h_out + row * C + j * 8) = pack8<T>(o);
+    }
+  }
+}
+
+// out = a + b + bias[c]: the ResNet block's output (shortcut + second conv + the conv biases) in one pass
+template <typename T>
+__global__ void __launch_bounds__(256)
+residual_bias_add_kernel(const T* a, const T* b, const T* __restrict__ bias, T* out, unsigned total, unsigned V) {
+  // 32-bit index arithmetic (the launcher checks rows * C / 8 < 2^31)
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 4 * stride) {
+    uint4 ra[4], rb[4], rc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned k = i + u * stride;
+      if (k < total) {
+        ra[u] = *reinterpret_cast<const uint4*>(a + (size_t)k * 8);
+        rb[u] = *reinterpret_cast<const uint4*>(b + (size_t)k * 8);
+        rc[u] = ldg16(bias + (k % V) * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned k = i + u * stride;
+      if (k < total) {
+        float fa[8], fb[8], fc[8], o[8];
+        unpack8<T>(ra[u], fa);
+        unpack8<T>(rb[u], fb);
+        unpack8<T>(rc[u], fc);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fa[e] + (fb[e] + fc[e]);
+        *reinterpret_cast<uint4*>(out + (size_t)k * 8) = pack8<T>(o);
+      }
     }
   }
 }
@@ -90,6 +139,7 @@ add_layer_norm_kernel(const T* x, const T* delta, const T* __restrict__ gamma, c
 // Thread layout of both kernels: V = C / 8 vector columns, R pixel rows in flight; thread (r, col) owns channels
 // [8 col, 8 col + 8) of pixels p0 + r, p0 + r + R, ...   A group (C / groups channels, 10 ... 80 here) is not aligned to
 // the 8-channel vectors, so statistics are kept per channel and folded into groups in shared memory.
+constexpr int kGnUnroll = 8;
 struct GnGeometry {
   int V, R, threads, chunks_stats, chunks_apply;   // threads = V * R rounded up to whole warps (the rest idle in the loops)
 };
@@ -97,26 +147,26 @@ struct GnGeometry {
 __host__ inline GnGeometry gn_geometry(int N, long long HW, int C) {
   GnGeometry g;
   g.V = C / 8;
-  g.R = g.V >= 384 ? 1 : 384 / g.V;
+  g.R = g.V >= 256 ? 1 : 256 / g.V;
   if ((long long)g.R > HW) g.R = (int)HW;
   g.threads = (g.V * g.R + 31) & ~31;
   const long long max_chunks = (HW + g.R - 1) / g.R;
   const long long frame_bytes = HW * C * 2;
-  // at least two CTAs per SM over the whole grid, and no CTA streaming much less than bytes_per_cta
+  // at least four CTAs per SM over the whole grid, and no CTA streaming much less than bytes_per_cta
   auto pick = [&](long long bytes_per_cta, long long cap) {
-    long long c = (2 * 148 + N - 1) / N;
+    long long c = (4 * 148 + N - 1) / N;
     if (frame_bytes / bytes_per_cta > c) c = frame_bytes / bytes_per_cta;
     if (c > cap) c = cap;
     if (c > max_chunks) c = max_chunks;
     return (int)(c < 1 ? 1 : c);
   };
-  g.chunks_stats = pick(128 << 10, 64);    // <= 64 partials per (frame, group): merged by two lane-strided passes
+  g.chunks_stats = pick(64 << 10, 128);    // <= 128 partials per (frame, group): merged by four lane-strided passes
   g.chunks_apply = pick(64 << 10, 65535);
   return g;
 }
 
 template <typename T>
-__global__ void gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ pre_bias, float2* __restrict__ partial,
+__global__ void __launch_bounds__(512) gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ pre_bias, float2* __restrict__ partial,
                                 long long HW, int C, int groups, int R, int chunks) {
   extern __shared__ float sh[];  // [2][R][C] per-channel sums and sums of squares
   const int V = C >> 3, tid = threadIdx.x, col = tid % V, r = tid / V;
@@ -125,34 +175,29 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ p
   const long long P = (HW + chunks - 1) / chunks;
   const long long p0 = chunk * P, p1 = active ? (p0 + P < HW ? p0 + P : HW) : 0;
   float pb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (pre_bias && active) unpack8<T>(*reinterpret_cast<const uint4*>(pre_bias + (long long)n * C + col * 8), pb);
+  if (pre_bias && active) unpack8<T>(ldg16(pre_bias + (long long)n * C + col * 8), pb);
   float s[8], ss[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
   const T* base = x + ((long long)n * HW) * C + col * 8;
-  long long p = p0 + r;
-  for (; p + 3LL * R < p1; p += 4LL * R) {  // four independent 16-byte loads in flight per thread
-    uint4 raw[4];
+  for (long long p = p0 + r; p < p1; p += (long long)kGnUnroll * R) {  // kGnUnroll independent 16-byte loads in flight
+    uint4 raw[kGnUnroll];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) raw[u] = *reinterpret_cast<const uint4*>(base + (p + (long long)u * R) * C);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float f[8];
-      unpack8<T>(raw[u], f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float val = pre_bias ? to_f32(from_f32<T>(f[e] + pb[e])) : f[e];
-        s[e] += val; ss[e] = fmaf(val, val, ss[e]);
-      }
+    for (int u = 0; u < kGnUnroll; ++u) {
+      const long long pp = p + (long long)u * R;
+      raw[u] = pp < p1 ? *reinterpret_cast<const uint4*>(base + pp * C) : make_uint4(0, 0, 0, 0);
     }
-  }
-  for (; p < p1; p += R) {
-    float f[8];
-    unpack8<T>(*reinterpret_cast<const uint4*>(base + p * C), f);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float val = pre_bias ? to_f32(from_f32<T>(f[e] + pb[e])) : f[e];
-      s[e] += val; ss[e] = fmaf(val, val, ss[e]);
+    for (int u = 0; u < kGnUnroll; ++u) {
+      if (p + (long long)u * R < p1) {
+        float f[8];
+        unpack8<T>(raw[u], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float val = pre_bias ? to_f32(from_f32<T>(f[e] + pb[e])) : f[e];
+          s[e] += val; ss[e] = fmaf(val, val, ss[e]);
+        }
+      }
     }
   }
   float* sh_s = sh;
@@ -177,22 +222,22 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ p
 }
 
 template <typename T>
-__global__ void gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ pre_bias, const float2* __restrict__ partial,
+__global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ pre_bias, const float2* __restrict__ partial,
                                 const T* __restrict__ gamma, const T* __restrict__ beta, T* __restrict__ y, long long HW,
                                 int C, int groups, int R, int chunks_stats, int chunks, float eps, int silu) {
   __shared__ float sh_mean[64], sh_rstd[64];
   const int V = C >> 3, tid = threadIdx.x, col = tid % V, r = tid / V;
   const bool active = r < R;   // the block is padded to whole warps (every warp takes part in the merge below)
   const int n = blockIdx.y, chunk = blockIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  // merge the per-chunk (mean, M2) partials of this frame: warp per group, lanes over chunks (chunks_stats <= 64)
+  // merge the per-chunk (mean, M2) partials of this frame: warp per group, lanes over chunks (chunks_stats <= 128)
   {
     const int gs = C / groups;
     const long long Ps = (HW + chunks_stats - 1) / chunks_stats;
     for (int g = warp; g < groups; g += nwarps) {
-      float cw[2], mw[2], m2w[2];
+      float cw[4], mw[4], m2w[4];
       float wsum = 0.f;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 4; ++u) {
         const int c = lane + 32 * u;
         cw[u] = 0.f; mw[u] = 0.f; m2w[u] = 0.f;
         if (c < chunks_stats) {
@@ -206,7 +251,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ p
       const float mean = warp_sum(wsum) / total;
       float m2 = 0.f;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) { const float dlt = mw[u] - mean; m2 += m2w[u] + cw[u] * dlt * dlt; }
+      for (int u = 0; u < 4; ++u) { const float dlt = mw[u] - mean; m2 += m2w[u] + cw[u] * dlt * dlt; }
       m2 = warp_sum(m2);
       if (lane == 0) { sh_mean[g] = mean; sh_rstd[g] = rsqrtf(m2 / total + eps); }
     }
@@ -218,15 +263,15 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ p
   {
     const int gs = C / groups;
     float gm[8], bt[8];
-    unpack8<T>(*reinterpret_cast<const uint4*>(gamma + col * 8), gm);
-    unpack8<T>(*reinterpret_cast<const uint4*>(beta + col * 8), bt);
+    unpack8<T>(ldg16(gamma + col * 8), gm);
+    unpack8<T>(ldg16(beta + col * 8), bt);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int g = (col * 8 + e) / gs;
       a[e] = sh_rstd[g] * gm[e];
       b[e] = bt[e] - sh_mean[g] * a[e];
     }
-    if (pre_bias) unpack8<T>(*reinterpret_cast<const uint4*>(pre_bias + (long long)n * C + col * 8), pb);
+    if (pre_bias) unpack8<T>(ldg16(pre_bias + (long long)n * C + col * 8), pb);
   }
   const long long P = (HW + chunks - 1) / chunks;
   const long long p0 = chunk * P, p1 = p0 + P < HW ? p0 + P : HW;
@@ -244,15 +289,19 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ p
     }
     return pack8<T>(o);
   };
-  long long p = p0 + r;
-  for (; p + 3LL * R < p1; p += 4LL * R) {
-    uint4 raw[4];
+  for (long long p = p0 + r; p < p1; p += (long long)kGnUnroll * R) {
+    uint4 raw[kGnUnroll];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) raw[u] = *reinterpret_cast<const uint4*>(base + (p + (long long)u * R) * C);
+    for (int u = 0; u < kGnUnroll; ++u) {
+      const long long pp = p + (long long)u * R;
+      raw[u] = pp < p1 ? *reinterpret_cast<const uint4*>(base + pp * C) : make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(obase + (p + (long long)u * R) * C) = transform(raw[u]);
+    for (int u = 0; u < kGnUnroll; ++u) {
+      const long long pp = p + (long long)u * R;
+      if (pp < p1) *reinterpret_cast<uint4*>(obase + pp * C) = transform(raw[u]);
+    }
   }
-  for (; p < p1; p += R) *reinterpret_cast<uint4*>(obase + p * C) = transform(*reinterpret_cast<const uint4*>(base + p * C));
 }
 
 template <typename T>
@@ -292,17 +341,48 @@ int launch_group_norm_nhwc(const void* x, const void* pre_bias, const void* gamm
 
 bool add_layer_norm_supported(int C) { return C % 8 == 0 && C / 8 <= 32 * kLnMaxVec; }
 
+template <typename T, int NV>
+static void launch_ln_nv(const void* x, const void* delta, const void* gamma, const void* beta, void* x_out, void* h_out,
+                         long long rows, int C, float eps, cudaStream_t stream) {
+  const unsigned blocks = (unsigned)((rows + kLnWarps - 1) / kLnWarps);
+  add_layer_norm_kernel<T, NV><<<blocks, kLnWarps * 32, 0, stream>>>((const T*)x, (const T*)delta, (const T*)gamma, (const T*)beta,
+                                                                   (T*)x_out, (T*)h_out, rows, C, eps);
+}
+
+template <typename T>
+static void launch_ln_t(const void* x, const void* delta, const void* gamma, const void* beta, void* x_out, void* h_out,
+                        long long rows, int C, float eps, cudaStream_t stream) {
+  const int nv = (C / 8 + 31) / 32;   // vectors per lane
+  if (nv <= 1) launch_ln_nv<T, 1>(x, delta, gamma, beta, x_out, h_out, rows, C, eps, stream);
+  else if (nv <= 2) launch_ln_nv<T, 2>(x, delta, gamma, beta, x_out, h_out, rows, C, eps, stream);
+  else if (nv <= 3) launch_ln_nv<T, 3>(x, delta, gamma, beta, x_out, h_out, rows, C, eps, stream);
+  else if (nv <= 5) launch_ln_nv<T, 5>(x, delta, gamma, beta, x_out, h_out, rows, C, eps, stream);
+  else launch_ln_nv<T, kLnMaxVec>(x, delta, gamma, beta, x_out, h_out, rows, C, eps, stream);
+}
+
 int launch_add_layer_norm(const void* x, const void* delta, const void* gamma, const void* beta, void* x_out, void* h_out,
                           long long rows, int C, float eps, int dtype, cudaStream_t stream) {
-  const unsigned blocks = (unsigned)((rows + kLnWarps - 1) / kLnWarps);
-  if (dtype == PAID_F16)
-    add_layer_norm_kernel<__half><<<blocks, kLnWarps * 32, 0, stream>>>((const __half*)x, (const __half*)delta, (const __half*)gamma,
-                                                                        (const __half*)beta, (__half*)x_out, (__half*)h_out, rows, C, eps);
-  else
-    add_layer_norm_kernel<__nv_bfloat16><<<blocks, kLnWarps * 32, 0, stream>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
-        (__nv_bfloat16*)x_out, (__nv_bfloat16*)h_out, rows, C, eps);
+  if (dtype == PAID_F16) launch_ln_t<__half>(x, delta, gamma, beta, x_out, h_out, rows, C, eps, stream);
+  else launch_ln_t<__nv_bfloat16>(x, delta, gamma, beta, x_out, h_out, rows, C, eps, stream);
   PAID_LAUNCH_CHECK("add_layer_norm_kernel");
+  return PAID_OK;
+}
+
+int launch_residual_bias_add(const void* a, const void* b, const void* bias, void* out, long long rows, int C, int dtype,
+                             cudaStream_t stream) {
+  const long long total = rows * (C / 8);
+  if (total >= (1LL << 31) - (148LL * 8 * 256 * 4)) return fail(PAID_EUNSUPPORTED, "paid_residual_bias_add: rows * C / 8 must be below 2^31");
+  long long blocks = (total + 256 * 4 - 1) / (256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  if (dtype == PAID_F16)
+    residual_bias_add_kernel<__half><<<(unsigned)blocks, 256, 0, stream>>>((const __half*)a, (const __half*)b, (const __half*)bias,
+                                                                          (__half*)out, (unsigned)total, (unsigned)(C / 8));
+  else
+    residual_bias_add_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>(
+        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, (unsigned)total,
+        (unsigned)(C / 8));
+  PAID_LAUNCH_CHECK("residual_bias_add_kernel");
   return PAID_OK;
 }
 

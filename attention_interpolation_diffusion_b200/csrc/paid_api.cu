@@ -261,6 +261,16 @@ int paid_add_layer_norm(const void* x, const void* delta, const void* gamma, con
   return launch_add_layer_norm(x, delta, gamma, beta, x_out, h_out, rows, C, eps, dtype, (cudaStream_t)cuda_stream);
 }
 
+int paid_residual_bias_add(const void* a, const void* b, const void* bias, void* out, int64_t rows, int32_t C,
+                           int32_t dtype, void* cuda_stream) {
+  if (!a || !b || !bias || !out) return fail(PAID_EINVAL, "paid_residual_bias_add: a, b, bias, out must be non-NULL");
+  if (rows <= 0 || C <= 0 || C % 8) return fail(PAID_EINVAL, "paid_residual_bias_add: rows > 0 and C a positive multiple of 8");
+  if (dtype != PAID_F16 && dtype != PAID_BF16) return fail(PAID_EINVAL, "paid_residual_bias_add: bad dtype");
+  if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)bias | (uintptr_t)out) & 15)
+    return fail(PAID_EINVAL, "paid_residual_bias_add: pointers must be 16-byte aligned");
+  return launch_residual_bias_add(a, b, bias, out, rows, C, dtype, (cudaStream_t)cuda_stream);
+}
+
 uint64_t paid_group_norm_workspace_bytes(int32_t N, int64_t HW, int32_t C, int32_t groups) {
   if (!group_norm_supported(C, groups)) return 0;
   return group_norm_workspace_bytes(N, HW, C, groups);

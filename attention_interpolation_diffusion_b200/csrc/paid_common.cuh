@@ -154,6 +154,8 @@ int launch_geglu(const void* h, void* out, long long M, int D, int dtype, cudaSt
 int launch_add_layer_norm(const void* x, const void* delta, const void* gamma, const void* beta, void* x_out, void* h_out,
                           long long rows, int C, float eps, int dtype, cudaStream_t stream);
 bool add_layer_norm_supported(int C);
+int launch_residual_bias_add(const void* a, const void* b, const void* bias, void* out, long long rows, int C, int dtype,
+                             cudaStream_t stream);
 int launch_group_norm_nhwc(const void* x, const void* pre_bias, const void* gamma, const void* beta, void* y, float* ws, int N,
                            long long HW, int C, int groups, float eps, int silu, int dtype, cudaStream_t stream);
 unsigned long long group_norm_workspace_bytes(int N, long long HW, int C, int groups);

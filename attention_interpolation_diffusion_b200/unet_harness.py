@@ -106,6 +106,19 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, temb):
+        if _native(x):
+            # the convs run without their biases (PyTorch adds a conv bias as a separate broadcast kernel): conv1's
+            # bias and the time embedding go into the load of the second norm, conv2's (and the shortcut's) bias into
+            # the residual add
+            from . import _cabi
+            c1, c2, sc = self.conv1, self.conv2, self.conv_shortcut
+            h = F.conv2d(group_norm(self.norm1, x, silu=True), c1.weight, None, padding=1)
+            tb = F.linear(F.silu(temb), self.time_emb_proj.weight, self.time_emb_proj.bias + c1.bias)
+            h = F.conv2d(group_norm(self.norm2, h, silu=True, pre_bias=tb), c2.weight, None, padding=1)
+            if not x.is_contiguous(memory_format=torch.channels_last):
+                x = x.contiguous(memory_format=torch.channels_last)
+            skip = x if sc is None else F.conv2d(x, sc.weight, None)
+            return _cabi.residual_bias_add(skip, h, c2.bias if sc is None else c2.bias + sc.bias)
         h = self.conv1(group_norm(self.norm1, x, silu=True))
         # h + time_emb[:, :, None, None] is folded into the load of the second norm
         h = self.conv2(group_norm(self.norm2, h, silu=True, pre_bias=self.time_emb_proj(F.silu(temb))))

@@ -159,6 +159,11 @@ int paid_group_norm_nhwc(const void* x, const void* pre_bias, const void* gamma,
                          uint64_t workspace_bytes, int32_t N, int64_t HW, int32_t C, int32_t groups, float eps,
                          int32_t silu, int32_t dtype, void* cuda_stream);
 
+/* out (rows,C) = a + b + bias(C): the ResNet block's output -- shortcut + second conv (run without its bias) + the
+ * conv biases -- in one pass instead of a broadcast bias add and a residual add.  out may alias a or b. */
+int paid_residual_bias_add(const void* a, const void* b, const void* bias, void* out, int64_t rows, int32_t C,
+                           int32_t dtype, void* cuda_stream);
+
 /* message for the last non-OK status returned on this thread ("" if none) */
 const char* paid_attn_last_error(void);
 

@@ -468,3 +468,15 @@ def test_unet_forward_native_glue_equals_torch_glue(cabi):
             finally:
                 U.NATIVE_GLUE = True
         check(outs[(aid, True)], outs[(aid, False)], ("native glue vs torch glue", aid), rel=5e-3, maxabs=5e-2)
+
+
+def test_residual_bias_add_against_torch(cabi):
+    torch.manual_seed(8)
+    for (N, C, H, W), dt in (((7, 320, 128, 128), torch.float16), ((2, 1280, 32, 32), torch.float16), ((1, 64, 3, 5), torch.bfloat16)):
+        a = torch.randn(N, C, H, W, device="cuda").to(dt).contiguous(memory_format=torch.channels_last)
+        b = torch.randn(N, C, H, W, device="cuda").to(dt).contiguous(memory_format=torch.channels_last)
+        bias = torch.randn(C, device="cuda").to(dt)
+        out = cabi.residual_bias_add(a, b, bias)
+        ref = a.float() + (b.float() + bias.float()[None, :, None, None])
+        assert out.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(out, ref.to(dt)), (N, C, H, W, dt)          # one rounding of the fp32 sum
