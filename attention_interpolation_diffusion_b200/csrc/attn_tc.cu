@@ -1,5 +1,5 @@
-// Interpolated attention core on the 5th-generation tensor cores (head_dim 64, or any multiple of 8 below 64
-// zero-padded to 64 by the TMA unit: SD1.5's 64x64 level has head_dim 40).
+// Interpolated attention core on the 5th-generation tensor cores: head_dim 64 (SDXL), and any multiple of 8 up to 192
+// as DT = ceil(head_dim / 64) chunks of 64 columns, the last one zero-padded by the TMA unit (SD1.5: 40, 80, 160).
 //
 // Replaces, per attention layer, the reference's endpoint replication, head split, [self ; endpoint]
 // concatenations, the two materialised softmax(QK^T) matrices, the two P.V products and the alpha-lerp
@@ -43,18 +43,24 @@ constexpr int BM = 128;          // rows per Q tile
 // one CTA per SM whose two Q tiles share every K/V tile (half the K/V traffic from L2 to shared memory).
 constexpr int BN = 64;           // keys per step
 constexpr int ST = 8;            // K/V ring stages
-constexpr int Q_BYTES = BM * D * 2;    // 16 KB
-constexpr int KV_BYTES = BN * D * 2;   // 16 KB
-template <int QT> struct Shape {
-  static constexpr int kStages = QT == 2 ? ST : 5;   // K/V ring stages (two CTAs per SM share 227 KB when QT = 1)
-  static constexpr int kSmemBytes = 1024 + QT * Q_BYTES + kStages * 2 * KV_BYTES + 512;
+constexpr int Q_BYTES = BM * D * 2;    // 16 KB: one 64-column chunk of a Q tile
+constexpr int KV_BYTES = BN * D * 2;   //  8 KB: one 64-column chunk of a K or V tile
+// DT = 64-column chunks of the head dimension (1: head_dim <= 64, 2: <= 128, 3: <= 192).  A chunk is one 128-byte
+// swizzled shared-memory tile per operand: Q K^T accumulates over the chunks (K dimension), P V is issued once per
+// chunk (N = 64 each) into adjacent accumulator columns, so every MMA and descriptor is the head_dim-64 one.
+// DT > 1 needs 128 + 2 * 64 DT > 256 TMEM columns: one CTA per SM, QT = 1 only.
+template <int QT, int DT> struct Shape {
+  static_assert(DT == 1 || QT == 1, "wide heads run with one Q tile per CTA");
+  static constexpr int kStages = DT == 3 ? 3 : (QT == 2 ? ST : 5);   // K/V ring stages (227 KB per SM)
+  static constexpr int kSmemBytes = 1024 + QT * DT * Q_BYTES + kStages * 2 * DT * KV_BYTES + 512;
   static constexpr int kThreads = 128 * (1 + QT);   // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1..QT: softmax
-  static constexpr int kCtasPerSm = QT == 2 ? 1 : 2;
+  static constexpr int kCtasPerSm = (QT == 2 || DT > 1) ? 1 : 2;
   // setmaxnreg split of the register file among the CTA's warpgroups (per-CTA budget 64K / kCtasPerSm)
   static constexpr int kRegsControl = 56;
   static constexpr int kRegsSoftmax = QT == 2 ? 224 : 200;
-  static constexpr uint32_t kTmemCols = 256 * QT;
+  static constexpr uint32_t kTmemCols = DT == 1 ? 256 * QT : 512;
   static constexpr uint32_t kTmemAcc = 128 * QT;     // S buffers first (2 x 64 columns per tile), accumulators after
+  static constexpr uint32_t kAccTile = 128 * DT;     // accumulator columns per Q tile: 2 streams x 64 DT
 };
 constexpr uint32_t TMEM_S = 0;
 constexpr float kRescaleThreshold = 8.f;  // log2 units: rescale an accumulator only when its max grew by > 2^8
@@ -102,20 +108,22 @@ __device__ __forceinline__ int frame_of_block(int z, int N) {
   return z < N - 2 ? z + 1 : (z == N - 2 ? 0 : N - 1);
 }
 
-template <typename T, int QT>
-__global__ void __launch_bounds__(Shape<QT>::kThreads, Shape<QT>::kCtasPerSm)
+template <typename T, int QT, int DT>
+__global__ void __launch_bounds__(Shape<QT, DT>::kThreads, Shape<QT, DT>::kCtasPerSm)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ CUtensorMap tmK2,
                const __grid_constant__ CUtensorMap tmV2, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int ST = Shape<QT>::kStages;           // (shadows the namespace constant: ring depth of this variant)
-  constexpr uint32_t TMEM_ACC = Shape<QT>::kTmemAcc;
-  uint8_t* sQ = smem;                              // [QT][128][64]
-  uint8_t* sK = sQ + QT * Q_BYTES;                 // [ST][64][64]
-  uint8_t* sV = sK + ST * KV_BYTES;                // [ST][64][64]
-  Barriers* bar = reinterpret_cast<Barriers*>(sV + ST * KV_BYTES);
+  using SH = Shape<QT, DT>;
+  constexpr int ST = SH::kStages;                  // (shadows the namespace constant: ring depth of this variant)
+  constexpr uint32_t TMEM_ACC = SH::kTmemAcc;
+  constexpr int QTILE = DT * Q_BYTES, KVTILE = DT * KV_BYTES;   // bytes of one Q / K / V tile (DT chunks)
+  uint8_t* sQ = smem;                              // [QT][DT][128][64]
+  uint8_t* sK = sQ + QT * QTILE;                   // [ST][DT][64][64]
+  uint8_t* sV = sK + ST * KVTILE;                  // [ST][DT][64][64]
+  Barriers* bar = reinterpret_cast<Barriers*>(sV + ST * KVTILE);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = frame_of_block(blockIdx.z, a.N), head = blockIdx.y, row0 = blockIdx.x * (QT * BM);
@@ -138,7 +146,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) { ptx::tmem_alloc(&bar->tmem_slot, Shape<QT>::kTmemCols); ptx::tmem_relinquish(); }
+  if (warp == 1) { ptx::tmem_alloc(&bar->tmem_slot, SH::kTmemCols); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -153,12 +161,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int total_steps = seg.count * tiles;
 
   if (warp < 4) {
-  ptx::setmaxnreg_dec<Shape<QT>::kRegsControl>();
+  ptx::setmaxnreg_dec<SH::kRegsControl>();
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (ptx::elect_one()) {
-      ptx::mbar_arrive_expect_tx(&bar->q_full, QT * Q_BYTES);
-      for (int t = 0; t < QT; ++t) ptx::tma_load_4d(sQ + t * Q_BYTES, &tmQ, &bar->q_full, 0, head, row0 + t * BM, n);
+      ptx::mbar_arrive_expect_tx(&bar->q_full, QT * QTILE);
+      for (int t = 0; t < QT; ++t)
+        for (int c = 0; c < DT; ++c)
+          ptx::tma_load_4d(sQ + t * QTILE + c * Q_BYTES, &tmQ, &bar->q_full, c * D, head, row0 + t * BM, n);
       int j = 0;
       for (int g = 0; g < seg.count; ++g) {
         const int slot = seg.slot[g];
@@ -169,11 +179,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const int s = j % ST;
           const uint32_t ph = (j / ST) & 1;
           ptx::mbar_wait(&bar->k_empty[s], ph ^ 1);
-          ptx::mbar_arrive_expect_tx(&bar->k_full[s], KV_BYTES);
-          ptx::tma_load_4d(sK + s * KV_BYTES, mk, &bar->k_full[s], 0, head, i * BN, fr);
+          ptx::mbar_arrive_expect_tx(&bar->k_full[s], KVTILE);
+          for (int c = 0; c < DT; ++c)
+            ptx::tma_load_4d(sK + s * KVTILE + c * KV_BYTES, mk, &bar->k_full[s], c * D, head, i * BN, fr);
           ptx::mbar_wait(&bar->v_empty[s], ph ^ 1);
-          ptx::mbar_arrive_expect_tx(&bar->v_full[s], KV_BYTES);
-          ptx::tma_load_4d(sV + s * KV_BYTES, mv, &bar->v_full[s], 0, head, i * BN, fr);
+          ptx::mbar_arrive_expect_tx(&bar->v_full[s], KVTILE);
+          for (int c = 0; c < DT; ++c)
+            ptx::tma_load_4d(sV + s * KVTILE + c * KV_BYTES, mv, &bar->v_full[s], c * D, head, i * BN, fr);
         }
       }
     }
@@ -185,11 +197,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       constexpr uint32_t idesc_pv = ptx::make_idesc(BM, D, fmt, 1);   // acc += P V : V is N(=d)-contiguous
       const uint32_t q_addr = ptx::smem_u32(sQ), k_addr = ptx::smem_u32(sK), v_addr = ptx::smem_u32(sV);
       auto issue_qk = [&](int t, int b, int s) {
-        const uint64_t qd = ptx::make_smem_desc_sw128(q_addr + t * Q_BYTES, 16, 1024);
-        const uint64_t kd = ptx::make_smem_desc_sw128(k_addr + s * KV_BYTES, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          ptx::mma_ss(tmem + TMEM_S + (t * 2 + b) * BN, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+        for (int c = 0; c < DT; ++c) {   // the head dimension is the K dimension of this product: accumulate over chunks
+          const uint64_t qd = ptx::make_smem_desc_sw128(q_addr + t * QTILE + c * Q_BYTES, 16, 1024);
+          const uint64_t kd = ptx::make_smem_desc_sw128(k_addr + s * KVTILE + c * KV_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k)
+            ptx::mma_ss(tmem + TMEM_S + (t * 2 + b) * BN, qd + 2 * k, kd + 2 * k, idesc_qk, (c | k) != 0);
+        }
       };
       // prologue: scores of steps 0 and 1
       ptx::mbar_wait(&bar->q_full, 0);
@@ -215,12 +230,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
             for (int st = 0; st < 2; ++st) {
               if (!(feeds & (1 << st))) continue;
-              const uint32_t acc = tmem + TMEM_ACC + t * 128 + st * D;  // 2 streams x 64 columns per tile
 #pragma unroll
-              for (int k = 0; k < BN / 16; ++k) {
-                // 16 keys per MMA: 8 packed columns of P, 16 rows (2048 B) of the V tile
-                const uint64_t vd = ptx::make_smem_desc_sw128(v_addr + s * KV_BYTES + k * 2048, 16, 1024);
-                ptx::mma_ts(acc, p_t + k * 8, vd, idesc_pv, started[st] || k != 0);
+              for (int c = 0; c < DT; ++c) {   // one N = 64 product per chunk of the head dimension
+                const uint32_t acc = tmem + TMEM_ACC + t * SH::kAccTile + (st * DT + c) * D;  // 2 streams x DT x 64 columns
+#pragma unroll
+                for (int k = 0; k < BN / 16; ++k) {
+                  // 16 keys per MMA: 8 packed columns of P, 16 rows (2048 B) of the V chunk
+                  const uint64_t vd = ptx::make_smem_desc_sw128(v_addr + s * KVTILE + c * KV_BYTES + k * 2048, 16, 1024);
+                  ptx::mma_ts(acc, p_t + k * 8, vd, idesc_pv, started[st] || k != 0);
+                }
               }
             }
             ptx::tc_commit(&bar->pv_done[t]);     // accumulators of tile t include step j
@@ -239,13 +257,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   }
   } else {
-    ptx::setmaxnreg_inc<Shape<QT>::kRegsSoftmax>();
+    ptx::setmaxnreg_inc<SH::kRegsSoftmax>();
     // ================================ softmax warpgroups ==========================
     const int t = (warp - 4) >> 2;   // Q tile of this warpgroup
     const int quad = warp & 3;       // TMEM lane quadrant of this warp
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t s_base = tmem + lane_base + TMEM_S + t * 2 * BN;
-    const uint32_t acc_addr = tmem + lane_base + TMEM_ACC + t * 128;
+    const uint32_t acc_addr = tmem + lane_base + TMEM_ACC + t * SH::kAccTile;
     const float sl2 = a.scale_log2;
     float m_st[2] = {-INFINITY, -INFINITY}, l_st[2] = {0.f, 0.f};  // per stream, m in raw-score units
     bool started[2] = {false, false};
@@ -299,9 +317,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int st = 0; st < 2; ++st) {
               if (!(feeds & (1 << st))) continue;
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
+              for (int h = 0; h < 2 * DT; ++h) {
                 uint32_t o[32];
-                ptx::tmem_ld32(acc_addr + st * D + h * 32, o);
+                ptx::tmem_ld32(acc_addr + st * DT * D + h * 32, o);
                 ptx::tmem_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 32; e += 2) {
@@ -309,7 +327,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                                              make_float2(alpha, alpha));
                   o[e] = __float_as_uint(r.x); o[e + 1] = __float_as_uint(r.y);
                 }
-                ptx::tmem_st32(acc_addr + st * D + h * 32, o);
+                ptx::tmem_st32(acc_addr + st * DT * D + h * 32, o);
               }
             }
           }
@@ -366,7 +384,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int row = row0 + t * BM + quad * 32 + lane;
     T* dst = (T*)a.out + ((long long)n * a.S + row) * (a.heads * a.head_dim) + head * a.head_dim;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 2 * DT; ++h) {
+      if (h * 32 >= a.head_dim) break;   // padded columns
       float acc[32];
 #pragma unroll
       for (int e = 0; e < 32; ++e) acc[e] = 0.f;
@@ -374,7 +393,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int st = 0; st < 2; ++st) {
         if (!active[st]) continue;  // CTA-uniform
         uint32_t o[32];
-        ptx::tmem_ld32(acc_addr + st * D + h * 32, o);
+        ptx::tmem_ld32(acc_addr + st * DT * D + h * 32, o);
         ptx::tmem_wait_ld();
 #pragma unroll
         for (int e = 0; e < 32; ++e) acc[e] = fmaf(cf[st], __uint_as_float(o[e]), acc[e]);
@@ -401,13 +420,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) { __syncwarp(); ptx::tmem_dealloc(tmem, Shape<QT>::kTmemCols); }
+  if (warp == 1) { __syncwarp(); ptx::tmem_dealloc(tmem, SH::kTmemCols); }
 }
 
-template <typename T, int QT>
+template <typename T, int QT, int DT>
 int launch_t(const CUtensorMap* maps, const TcArgs& ta, cudaStream_t stream) {
-  auto kern = attn_tc_kernel<T, QT>;
-  constexpr int SMEM_BYTES = Shape<QT>::kSmemBytes, NUM_THREADS = Shape<QT>::kThreads;
+  auto kern = attn_tc_kernel<T, QT, DT>;
+  constexpr int SMEM_BYTES = Shape<QT, DT>::kSmemBytes, NUM_THREADS = Shape<QT, DT>::kThreads;
+  static_assert(SMEM_BYTES <= 232448, "shared memory per CTA");
   static bool configured = false;
   if (!configured) {
     PAID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -425,8 +445,11 @@ int launch_t(const CUtensorMap* maps, const TcArgs& ta, cudaStream_t stream) {
 }  // namespace
 
 bool attn_tc_supported(const CoreArgs& a) {
-  const char* nopad = getenv("PAID_ATTN_NO_PAD");   // debugging: serve head_dim < 64 with the generic kernel
-  const bool padded_ok = a.head_dim < D && a.head_dim >= 16 && a.head_dim % 8 == 0 && !(nopad && nopad[0] == '1');
+  const char* nopad = getenv("PAID_ATTN_NO_PAD");   // debugging: serve head_dim != 64 with the generic kernel
+  const char* cap = getenv("PAID_ATTN_MAX_TC_HEAD_DIM");   // debugging: larger head_dim goes to the generic kernel
+  const int max_hd = cap ? atoi(cap) : 3 * D;
+  const bool padded_ok = a.head_dim != D && a.head_dim >= 16 && a.head_dim <= 3 * D && a.head_dim <= max_hd &&
+                         a.head_dim % 8 == 0 && !(nopad && nopad[0] == '1');
   return (a.head_dim == D || padded_ok) && a.heads <= 65535 && a.N <= 65535 &&
          !(((uintptr_t)a.q | (uintptr_t)a.k | (uintptr_t)a.v | (uintptr_t)a.out | (uintptr_t)a.k1 | (uintptr_t)a.v1 |
             (uintptr_t)a.k2 | (uintptr_t)a.v2) & 15);
@@ -434,11 +457,11 @@ bool attn_tc_supported(const CoreArgs& a) {
 
 int launch_attn_tc(const CoreArgs& a, cudaStream_t stream) {
   CUtensorMap maps[7];
-  const int hd = a.head_dim;  // <= D; the box of every map is D wide (zero fill beyond hd)
+  const int hd = a.head_dim;  // the box of every map is D = 64 wide; the TMA unit zero-fills columns >= hd
   const long long C = (long long)a.heads * hd;
   int st = make_tmap_heads(&maps[0], a.q, a.dtype, a.N, a.S, a.heads, hd, (long long)a.S * C, BM);
   // a driver that rejects a box wider than the tensor: nothing was launched, the caller falls back (core_dispatch)
-  if (st != PAID_OK) return hd < D ? PAID_EUNSUPPORTED : st;
+  if (st != PAID_OK) return hd % D ? PAID_EUNSUPPORTED : st;
   const long long kv_frames = a.stride0 ? a.N : 1;
   if ((st = make_tmap_heads(&maps[1], a.k, a.dtype, kv_frames, a.L, a.heads, hd, a.stride0, BN)) != PAID_OK) return st;
   if ((st = make_tmap_heads(&maps[2], a.v, a.dtype, kv_frames, a.L, a.heads, hd, a.stride0, BN)) != PAID_OK) return st;
@@ -466,9 +489,13 @@ int launch_attn_tc(const CoreArgs& a, cudaStream_t stream) {
   ta.accumulate = a.accumulate; ta.out_scale = a.out_scale; ta.out_frame_scale = a.out_frame_scale;
   const char* force = getenv("PAID_ATTN_QT");
   const bool single_tile = !(force && force[0] == '2');
+  if (hd > 2 * D)
+    return a.dtype == PAID_F16 ? launch_t<__half, 1, 3>(maps, ta, stream) : launch_t<__nv_bfloat16, 1, 3>(maps, ta, stream);
+  if (hd > D)
+    return a.dtype == PAID_F16 ? launch_t<__half, 1, 2>(maps, ta, stream) : launch_t<__nv_bfloat16, 1, 2>(maps, ta, stream);
   if (single_tile)
-    return a.dtype == PAID_F16 ? launch_t<__half, 1>(maps, ta, stream) : launch_t<__nv_bfloat16, 1>(maps, ta, stream);
-  return a.dtype == PAID_F16 ? launch_t<__half, 2>(maps, ta, stream) : launch_t<__nv_bfloat16, 2>(maps, ta, stream);
+    return a.dtype == PAID_F16 ? launch_t<__half, 1, 1>(maps, ta, stream) : launch_t<__nv_bfloat16, 1, 1>(maps, ta, stream);
+  return a.dtype == PAID_F16 ? launch_t<__half, 2, 1>(maps, ta, stream) : launch_t<__nv_bfloat16, 2, 1>(maps, ta, stream);
 }
 
 }  // namespace paid

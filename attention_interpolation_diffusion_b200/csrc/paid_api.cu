@@ -135,11 +135,12 @@ static int core_dispatch(const CoreArgs& a, uint32_t flags, cudaStream_t stream)
   ProfileState& ps = prof();
   const size_t before = ps.on ? ps.used.size() : 0;
   int st;
-  static std::atomic<bool> pad_rejected{false};  // zero-padded head_dim < 64 needs a box wider than the tensor
-  if (!(flags & PAID_FLAG_GENERIC_KERNELS) && attn_tc_supported(a) && !(a.head_dim < 64 && pad_rejected.load())) {
-    *last_kernel_slot() = a.head_dim < 64 ? "tcgen05-padded" : "tcgen05";
+  static std::atomic<bool> pad_rejected{false};  // a zero-padded head_dim needs a TMA box wider than the tensor
+  const bool padded = a.head_dim % 64 != 0;
+  if (!(flags & PAID_FLAG_GENERIC_KERNELS) && attn_tc_supported(a) && !(padded && pad_rejected.load())) {
+    *last_kernel_slot() = padded ? "tcgen05-padded" : "tcgen05";
     st = launch_attn_tc(a, stream);
-    if (st == PAID_EUNSUPPORTED && a.head_dim < 64) {  // descriptor refused before any launch: other CUDA kernel family
+    if (st == PAID_EUNSUPPORTED && padded) {  // descriptor refused before any launch: other CUDA kernel family
       pad_rejected.store(true);
       *last_kernel_slot() = "generic";
       st = launch_attn_generic(a, stream);

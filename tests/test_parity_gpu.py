@@ -95,15 +95,16 @@ def test_sdxl_geometry_against_oracle(cabi, m, fused):
         check(y, ref, (m, fused, L), rel=1e-3)
 
 
+@pytest.mark.parametrize("S,C", [(1024, 320), (1024, 640), (256, 1280)], ids=["d40", "d80", "d160"])
 @pytest.mark.parametrize("m,fused", MODES)
-def test_sd15_geometry_padded_head_dim(cabi, m, fused):
-    """SD1.5 64x64 level (C=320, 8 heads of 40; S reduced to 1024 so the oracle finishes in seconds), self and cross:
-    head_dim 40 runs on the tcgen05 kernel zero-padded to 64 by the TMA unit; it must agree with the oracle and
-    with the generic CUDA kernel, and bf16 must stay inside its gate."""
+def test_sd15_geometry_padded_head_dim(cabi, m, fused, S, C):
+    """SD1.5 levels (8 heads of 40 / 80 / 160; S of the 64x64 level reduced to 1024 so the oracle finishes in seconds),
+    self and cross: head_dim != 64 runs on the tcgen05 kernel as 1 / 2 / 3 chunks of 64 columns, the last one
+    zero-padded by the TMA unit; it must agree with the oracle and with the generic CUDA kernel, bf16 inside its gate."""
     mode = O.MODE_NAMES[m]
     for L in (None, 77):
-        w = O.make_layer(320, 320 if L is None else 768, 8, 51)
-        x, ctx = O.make_inputs(5, 1024, 320, L, 768, 51)
+        w = O.make_layer(C, C if L is None else 768, 8, 51)
+        x, ctx = O.make_inputs(5, S, C, L, 768, 51)
         coef = O.coefficients(5, 4, 4)
         y = run_layer(cabi, w, x, ctx, coef, mode, fused)
         kernel = cabi.last_kernel()
@@ -115,6 +116,30 @@ def test_sd15_geometry_padded_head_dim(cabi, m, fused):
         check(y, yg, (m, fused, L, "padded tcgen05 == generic"), rel=1e-3)
         yb = run_layer(cabi, w, x, ctx, coef, mode, fused, dtype=torch.bfloat16)
         check(yb, ref, (m, fused, L, "bf16"), rel=8 * REL, maxabs=8 * MAXABS)
+
+
+def test_wide_heads_rescale_and_determinism(cabi):
+    """head_dim 80 / 128 / 160 / 192 on the chunked tcgen05 kernel: growing logits force the accumulator rescale over
+    every chunk; repeated launches are bit-identical; the result matches the generic kernel."""
+    for d in (80, 128, 160, 192):
+        N, S, L, h = 4, 300, 520, 2
+        torch.manual_seed(d)
+        q = torch.randn(N, S, h * d)
+        k = torch.randn(N, L, h * d) * torch.linspace(0.2, 5.0, L).view(1, L, 1)
+        v = torch.randn(N, L, h * d)
+        coef = O.coefficients(N, 2, 2)
+        ends = tuple(rounded(t) for t in (k[0], v[0], k[-1], v[-1]))
+        for m, fused in MODES + [("plain", False)]:
+            mode = O.MODE_NAMES[m]
+            out = cabi.attn_core(dev(q), dev(k), dev(v), coef.cuda(), h, mode, fused)
+            assert cabi.last_kernel() in ("tcgen05", "tcgen05-padded", "generic")
+            again = cabi.attn_core(dev(q), dev(k), dev(v), coef.cuda(), h, mode, fused)
+            assert torch.equal(out, again), (d, m, fused)
+            ref = O._direct_core(rounded(q), rounded(k), rounded(v), ends, coef, mode, fused, d ** -0.5, h)
+            check(out.float().cpu(), ref, ("wide head", d, m, fused), rel=2e-3)
+            if d <= 160:      # the generic kernels stop at head_dim 160
+                gen = cabi.attn_core(dev(q), dev(k), dev(v), coef.cuda(), h, mode, fused, flags=cabi.FLAG_GENERIC_KERNELS)
+                check(out.float().cpu(), gen.float().cpu(), ("wide head vs generic", d, m, fused), rel=2e-3)
 
 
 @pytest.mark.parametrize("m,fused", MODES)

@@ -8,6 +8,8 @@ for C, side in ((320, 128), (640, 64), (1280, 32), (2560, 32)):
     x = torch.randn(N, C, side, side, device="cuda").half().contiguous(memory_format=torch.channels_last)
     g = torch.ones(C, device="cuda").half(); b = torch.zeros(C, device="cuda").half()
     _cabi.group_norm_nhwc(x, g, b, 32, 1e-5, True, None)                     # gn_stats + gn_apply
+    if C == 320:
+        _cabi.residual_bias_add(x, x.clone(memory_format=torch.channels_last), b)
 for S, C in ((4096, 640), (1024, 1280)):
     x = torch.randn(N, S, C, device="cuda").half(); d = torch.randn_like(x)
     g = torch.ones(C, device="cuda").half(); b = torch.zeros(C, device="cuda").half()
