@@ -167,18 +167,47 @@ class _InterpolatedIPAttnProcessor(InterpolatedAttnProcessor):
     def _parts(self, attn, hidden_states, encoder_hidden_states, attention_mask):
         check_unet_preconditions(attn, hidden_states, attention_mask)
         x = hidden_states
-        if self.shard is not None:
-            raise NotImplementedError("frame sharding of the IP-Adapter variants is not implemented")
-        if x.shape[0] != self.size or self.coef.numel() != self.size:
-            raise ValueError(f"batch size {x.shape[0]} / {self.coef.numel()} coefficients != processor size {self.size}")
+        sh = self.shard
+        frames = x.shape[0]
+        if sh is not None:
+            if frames != sh.local_frames or self.size != sh.num_frames:
+                raise ValueError(f"local batch {frames} / processor size {self.size} do not match the shard "
+                                 f"({sh.local_frames} of {sh.num_frames} frames)")
+        elif frames != self.size:
+            raise ValueError(f"batch size {frames} != processor size {self.size}")
+        if self.coef.numel() != self.size:
+            raise ValueError(f"{self.coef.numel()} coefficients != processor size {self.size}")
         text, ip = (None, None) if encoder_hidden_states is None else split_ip_states(
-            encoder_hidden_states, self.num_tokens, x.shape[0])
-        coef = _device_coef(self.coef, x.device)
+            encoder_hidden_states, self.num_tokens, frames)
+        coef = _device_coef(self.coef if sh is None else self.coef[sh.lo:sh.hi], x.device)
         src = x if text is None else text
         q = _cabi.linear(x, attn.to_q.weight, flags=self.kernel_flags)
         k = _cabi.linear(src, attn.to_k.weight, flags=self.kernel_flags)
         v = _cabi.linear(src, attn.to_v.weight, flags=self.kernel_flags)
         return x, ip, coef, q, k, v
+
+    def _endpoints(self, k, v, need_begin: bool = True):
+        """Frame-sharded call: keyword arguments for ``attn_core`` that carry the endpoint K/V of the whole sequence
+        (rows of the local k / v on the ranks that own frame 0 / N-1, broadcast to the others -- the one collective of
+        the path, sharding.py).  Unsharded: the endpoints are rows 0 and -1 of the batch (no arguments)."""
+        sh = self.shard
+        if sh is None:
+            return {}
+        from .sharding import broadcast_endpoints
+        kv = torch.empty(4, k.shape[1], k.shape[2], dtype=k.dtype, device=k.device)
+        own_b, own_e = sh.rank == sh.begin_owner, sh.rank == sh.end_owner
+        if own_b and need_begin:
+            kv[0].copy_(k[0]), kv[1].copy_(v[0])
+        if own_e:
+            kv[2].copy_(k[-1]), kv[3].copy_(v[-1])
+        if not need_begin:
+            kv[0:2].zero_()            # never read by the kernel's consumers; keep the buffer defined
+        if sh.world_size > 1:
+            if need_begin:
+                broadcast_endpoints(kv, sh.begin_owner, sh.end_owner, sh.group)
+            else:
+                torch.distributed.broadcast(kv[2:4], src=sh.end_owner, group=sh.group)
+        return dict(kv_ext=kv, begin_frame=0 if own_b else -1, end_frame=k.shape[0] - 1 if own_e else -1)
 
     def _ip_kv(self, ip):
         return (_cabi.linear(ip, self.ip_attn.to_k_ip[0].weight, flags=self.kernel_flags),
@@ -197,11 +226,12 @@ class OuterInterpolatedIPAttnProcessor(_InterpolatedIPAttnProcessor):
         if not self.activated:
             return self.ip_attn(attn, hidden_states, encoder_hidden_states, attention_mask, temb)
         x, ip, coef, q, k, v = self._parts(attn, hidden_states, encoder_hidden_states, attention_mask)
-        hid = _cabi.attn_core(q, k, v, coef, attn.heads, _cabi.PAID_OUTER, self.is_fused, attn.scale, flags=self.kernel_flags)
+        hid = _cabi.attn_core(q, k, v, coef, attn.heads, _cabi.PAID_OUTER, self.is_fused, attn.scale, flags=self.kernel_flags,
+                              **self._endpoints(k, v))
         if ip is not None:
             kip, vip = self._ip_kv(ip)
             _cabi.attn_core(q, kip, vip, coef, attn.heads, _cabi.PAID_OUTER, self.is_fused, attn.scale, flags=self.kernel_flags,
-                            out=hid, accumulate=True, out_scale=float(self.scale[0]))
+                            out=hid, accumulate=True, out_scale=float(self.scale[0]), **self._endpoints(kip, vip))
         return self._out(attn, hid)
 
 
@@ -215,7 +245,8 @@ class InnerInterpolatedIPAttnProcessor(_InterpolatedIPAttnProcessor):
         if not self.activated:
             return self.ip_attn(attn, hidden_states, encoder_hidden_states, attention_mask, temb)
         x, ip, coef, q, k, v = self._parts(attn, hidden_states, encoder_hidden_states, attention_mask)
-        hid = _cabi.attn_core(q, k, v, coef, attn.heads, _cabi.PAID_INNER, self.is_fused, attn.scale, flags=self.kernel_flags)
+        hid = _cabi.attn_core(q, k, v, coef, attn.heads, _cabi.PAID_INNER, self.is_fused, attn.scale, flags=self.kernel_flags,
+                              **self._endpoints(k, v))
         if ip is not None:
             kip, vip = self._ip_kv(ip)
             _cabi.attn_core(q, kip, vip, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale, flags=self.kernel_flags,
@@ -231,11 +262,15 @@ class ScaleControlIPAttnProcessor(_InterpolatedIPAttnProcessor):
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
         x, ip, coef, q, k, v = self._parts(attn, hidden_states, encoder_hidden_states, attention_mask)
         if self.activated:
-            hid = _cabi.attn_core(q, k, v, coef, attn.heads, _cabi.PAID_OUTER, self.is_fused, attn.scale, flags=self.kernel_flags)
+            hid = _cabi.attn_core(q, k, v, coef, attn.heads, _cabi.PAID_OUTER, self.is_fused, attn.scale, flags=self.kernel_flags,
+                                  **self._endpoints(k, v))
         else:
             hid = _cabi.attn_core(q, k, v, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale, flags=self.kernel_flags)
         if ip is not None:
             kip, vip = self._ip_kv(ip[-1:].contiguous())          # the end image for every frame (ip[0][6:9])
+            if self.shard is not None:                            # ... which lives on the rank that owns frame N-1
+                kv = self._endpoints(kip, vip, need_begin=False)["kv_ext"]
+                kip, vip = kv[2:3], kv[3:4]
             _cabi.attn_core(q, kip, vip, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale, flags=self.kernel_flags,
                             out=hid, accumulate=True, out_frame_scale=coef, kv_broadcast=True)
         return self._out(attn, hid)

@@ -149,6 +149,7 @@ class InterpolationPipeline:
             elif isinstance(old, (OuterInterpolatedAttnProcessor, InnerInterpolatedAttnProcessor)):
                 old = old.original_attn
             attn_procs[name] = cls(t=t, size=size, is_fused=is_fused, alpha=alpha, beta=beta, ip_attn=old)
+            attn_procs[name].shard = self.shard
         self.unet.set_attn_processor(attn_procs)
         self._graphs.clear()
 
@@ -217,9 +218,16 @@ class InterpolationPipeline:
     def interpolate(self, latent_start, latent_end, embeds_start, embeds_end, negative_embeds, size: int = 7,
                     alpha: float = 4.0, beta: float = 4.0, guide_embeds=None, pooled_start=None, pooled_end=None,
                     pooled_negative=None, pooled_guide=None, num_inference_steps: int = 50,
-                    guidance_scale: Optional[float] = None, warmup_ratio: float = 0.5, coef: Optional[torch.Tensor] = None):
+                    guidance_scale: Optional[float] = None, warmup_ratio: float = 0.5, coef: Optional[torch.Tensor] = None,
+                    ip_start=None, ip_end=None, ip_negative=None):
         """N-frame AID / PAID in one batch.  latent_* (1,4,H,W); embeds_* (1,77,Cc); pooled_* (1,1280) for SDXL.
-        Interior frames take lerped embeddings, or ``guide_embeds`` when given (PAID).  Returns this rank's frames."""
+        Interior frames take lerped embeddings, or ``guide_embeds`` when given (PAID).  Returns this rank's frames.
+
+        Image-conditioned morphing (after ``load_aid_ip_adapter``; reference sdxl:2144-2197): ``ip_start`` / ``ip_end``
+        (1,T,Cc) are the projected IP-Adapter image tokens of the two endpoint images; frame i gets their lerp by c_i
+        (the reference's ``init == "linear"``), the unconditional pass ``ip_negative`` (default zeros).  The tokens
+        travel appended to the text embeddings (one of the two forms the reference's processors accept,
+        interpolation.py:259-266)."""
         g = self.unet.cfg.guidance_scale if guidance_scale is None else guidance_scale
         if coef is None:
             coef = generate_beta_tensor(size, alpha, beta)
@@ -236,6 +244,10 @@ class InterpolationPipeline:
 
         cond = frames(embeds_start, embeds_end, guide_embeds)
         uncond = negative_embeds.expand(size, -1, -1).contiguous()
+        if ip_start is not None:
+            ip_neg = torch.zeros_like(ip_start) if ip_negative is None else ip_negative
+            cond = torch.cat([cond, frames(ip_start, ip_end, None)], dim=1)
+            uncond = torch.cat([uncond, ip_neg.expand(size, -1, -1)], dim=1)
         pooled_c = pooled_u = None
         if self.unet.cfg.text_time:
             pooled_c = frames(pooled_start, pooled_end, pooled_guide)

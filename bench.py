@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--frames", type=int, default=0, help="total frames of the sequence (default 7 per GPU)")
     ap.add_argument("--atype", default="fused_outer", choices=["fused_outer", "fused_inner"])
     ap.add_argument("--denoise-steps", type=int, default=STEPS_PER_SEQUENCE)
+    ap.add_argument("--ip-tokens", type=int, default=0,
+                    help="image-conditioned morphing (BASELINE configs[4]): IP-Adapter processors with this many image "
+                         "tokens per frame (16 = ip-adapter-plus); 0 = text-only PAID")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly (for ncu launch lists)")
@@ -85,7 +88,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # synthetic inputs: seed 1002, N(0,1) latents and embeddings
 # ---------------------------------------------------------------------------------------------------------
-def make_host_inputs(cfg, dtype):
+def make_host_inputs(cfg, dtype, ip_tokens=0):
     import torch
     g = torch.Generator("cpu").manual_seed(1002)
     r = lambda *s: torch.randn(*s, generator=g).to(dtype).pin_memory() if torch.cuda.is_available() else torch.randn(*s, generator=g).to(dtype)
@@ -94,6 +97,8 @@ def make_host_inputs(cfg, dtype):
              embeds_end=r(1, 77, cc), negative_embeds=r(1, 77, cc), guide_embeds=r(1, 77, cc))
     if cfg.text_time:
         d.update(pooled_start=r(1, 1280), pooled_end=r(1, 1280), pooled_negative=r(1, 1280), pooled_guide=r(1, 1280))
+    if ip_tokens:
+        d.update(ip_start=r(1, ip_tokens, cc), ip_end=r(1, ip_tokens, cc))
     return d
 
 
@@ -240,7 +245,8 @@ def run_reference_arm(args):
 
 def workload_config(args, frames):
     name = {"sdxl": "SDXL 128x128 latent", "sd15": "SD1.5 64x64 latent", "tiny": "tiny test UNet"}[args.model]
-    return {"workload": f"{name}, {frames}-frame PAID (guide prompt), {args.atype} AID in all attention layers, "
+    ip = f" + IP-Adapter image morphing ({args.ip_tokens} image tokens per frame)" if args.ip_tokens else ""
+    return {"workload": f"{name}, {frames}-frame PAID (guide prompt){ip}, {args.atype} AID in all attention layers, "
                         f"{args.denoise_steps} steps, warmup_ratio {WARMUP_RATIO}, CFG (2 UNet passes/step)",
             "frames": frames, "frames_per_gpu": frames // max(args.gpus, 1), "denoise_steps": args.denoise_steps,
             "parallelism": f"frame-sharded x{args.gpus}" if args.gpus > 1 else "single GPU",
@@ -272,8 +278,13 @@ def run_own_arm(args):
     net = build_unet(args.model, dev, dtype, seed=1002)
     shard = FrameShard(rank, world, frames, None) if world > 1 else None
     pipe = InterpolationPipeline(net, shard=shard, use_cuda_graphs=not args.no_graphs)
-    pipe.load_aid(t=None, is_fused=True, atype=args.atype, size=frames, alpha=4, beta=4)
-    host = make_host_inputs(net.cfg, dtype)
+    if args.ip_tokens:
+        torch.manual_seed(1002)
+        pipe.load_aid_ip_adapter(num_tokens=args.ip_tokens, scale=1.0, t=None, is_fused=True, early=args.atype, size=frames,
+                                 alpha=4, beta=4)
+    else:
+        pipe.load_aid(t=None, is_fused=True, atype=args.atype, size=frames, alpha=4, beta=4)
+    host = make_host_inputs(net.cfg, dtype, args.ip_tokens)
     devin = {k: v.to(dev) for k, v in host.items()}
     kw = dict(size=frames, alpha=4.0, beta=4.0, num_inference_steps=args.denoise_steps, warmup_ratio=WARMUP_RATIO)
 

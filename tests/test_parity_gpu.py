@@ -505,3 +505,28 @@ def test_residual_bias_add_against_torch(cabi):
         ref = a.float() + (b.float() + bias.float()[None, :, None, None])
         assert out.is_contiguous(memory_format=torch.channels_last)
         assert torch.equal(out, ref.to(dt)), (N, C, H, W, dt)          # one rounding of the fp32 sum
+
+
+@pytest.mark.parametrize("early", ["fused_outer", "fused_inner", "scale_control"])
+def test_ip_pipeline_and_frame_shard(cabi, early):
+    """Image-conditioned morphing through the pipeline (BASELINE configs[4] shape of call: IP-Adapter processors in
+    every layer, image tokens appended to the text embeddings, N = 5 frames): finite, CUDA-graph replay equals eager,
+    and a single-rank frame shard (endpoint K/V of text AND image tokens routed through kv_ext) equals the unsharded run."""
+    from attention_interpolation_diffusion_b200.pipeline import InterpolationPipeline
+    from attention_interpolation_diffusion_b200.sharding import FrameShard
+    from attention_interpolation_diffusion_b200.unet_harness import build_unet
+    net = build_unet("tiny", "cuda", torch.float16, seed=5)
+    g = torch.Generator("cpu").manual_seed(12)
+    r = lambda *s: torch.randn(*s, generator=g).cuda().half()
+    args = dict(latent_start=r(1, 4, 16, 16), latent_end=r(1, 4, 16, 16), embeds_start=r(1, 77, 96), embeds_end=r(1, 77, 96),
+                negative_embeds=r(1, 77, 96), pooled_start=r(1, 1280), pooled_end=r(1, 1280), pooled_negative=r(1, 1280),
+                ip_start=r(1, 4, 96), ip_end=r(1, 4, 96), size=5, num_inference_steps=4)
+    outs = {}
+    for name, shard, graphs in (("eager", None, False), ("graphs", None, True), ("shard", FrameShard(0, 1, 5), False)):
+        pipe = InterpolationPipeline(net, shard=shard, use_cuda_graphs=graphs)
+        torch.manual_seed(0)                      # same random-init to_k_ip / to_v_ip for every variant
+        pipe.load_aid_ip_adapter(num_tokens=4, scale=0.7, t=None, is_fused=True, early=early, size=5, alpha=2, beta=2)
+        outs[name] = pipe.interpolate(**args).float().cpu()
+        assert torch.isfinite(outs[name]).all()
+    check(outs["graphs"], outs["eager"], (early, "graph replay vs eager"), rel=1e-3)
+    check(outs["shard"], outs["eager"], (early, "world-size-1 shard vs unsharded"), rel=2e-3)
