@@ -12,6 +12,8 @@
 //                           bias added on load: the ResNet time-embedding add).         bytes: 2 / element (one read)
 //   gn_apply_kernel       : merges the partials (Chan), y = (x - mean) * rstd * gamma + beta, optional SiLU.
 //                                                                                      bytes: 4 / element (read + write)
+#include <cstdlib>
+
 #include "paid_common.cuh"
 
 namespace paid {
@@ -139,7 +141,6 @@ residual_bias_add_kernel(const T* a, const T* b, const T* __restrict__ bias, T* 
 // Thread layout of both kernels: V = C / 8 vector columns, R pixel rows in flight; thread (r, col) owns channels
 // [8 col, 8 col + 8) of pixels p0 + r, p0 + r + R, ...   A group (C / groups channels, 10 ... 80 here) is not aligned to
 // the 8-channel vectors, so statistics are kept per channel and folded into groups in shared memory.
-constexpr int kGnUnroll = 8;
 struct GnGeometry {
   int V, R, threads, chunks_stats, chunks_apply;   // threads = V * R rounded up to whole warps (the rest idle in the loops)
 };
@@ -165,8 +166,9 @@ __host__ inline GnGeometry gn_geometry(int N, long long HW, int C) {
   return g;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(512) gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ pre_bias, float2* __restrict__ partial,
+// U = independent 16-byte loads in flight per thread; HB = has pre_bias; MAXT / MINB = launch bounds (register budget)
+template <typename T, int U, bool HB, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ pre_bias, float2* __restrict__ partial,
                                 long long HW, int C, int groups, int R, int chunks) {
   extern __shared__ float sh[];  // [2][R][C] per-channel sums and sums of squares
   const int V = C >> 3, tid = threadIdx.x, col = tid % V, r = tid / V;
@@ -175,26 +177,26 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const T* __restrict__ x, 
   const long long P = (HW + chunks - 1) / chunks;
   const long long p0 = chunk * P, p1 = active ? (p0 + P < HW ? p0 + P : HW) : 0;
   float pb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (pre_bias && active) unpack8<T>(ldg16(pre_bias + (long long)n * C + col * 8), pb);
+  if (HB && active) unpack8<T>(ldg16(pre_bias + (long long)n * C + col * 8), pb);
   float s[8], ss[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
   const T* base = x + ((long long)n * HW) * C + col * 8;
-  for (long long p = p0 + r; p < p1; p += (long long)kGnUnroll * R) {  // kGnUnroll independent 16-byte loads in flight
-    uint4 raw[kGnUnroll];
+  for (long long p = p0 + r; p < p1; p += (long long)U * R) {  // U independent 16-byte loads in flight
+    uint4 raw[U];
 #pragma unroll
-    for (int u = 0; u < kGnUnroll; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long long pp = p + (long long)u * R;
       raw[u] = pp < p1 ? *reinterpret_cast<const uint4*>(base + pp * C) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int u = 0; u < kGnUnroll; ++u) {
+    for (int u = 0; u < U; ++u) {
       if (p + (long long)u * R < p1) {
         float f[8];
         unpack8<T>(raw[u], f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float val = pre_bias ? to_f32(from_f32<T>(f[e] + pb[e])) : f[e];
+          const float val = HB ? to_f32(from_f32<T>(f[e] + pb[e])) : f[e];
           s[e] += val; ss[e] = fmaf(val, val, ss[e]);
         }
       }
@@ -221,8 +223,8 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const T* __restrict__ x, 
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ pre_bias, const float2* __restrict__ partial,
+template <typename T, int U, bool HB, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ pre_bias, const float2* __restrict__ partial,
                                 const T* __restrict__ gamma, const T* __restrict__ beta, T* __restrict__ y, long long HW,
                                 int C, int groups, int R, int chunks_stats, int chunks, float eps, int silu) {
   __shared__ float sh_mean[64], sh_rstd[64];
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x, 
       a[e] = sh_rstd[g] * gm[e];
       b[e] = bt[e] - sh_mean[g] * a[e];
     }
-    if (pre_bias) unpack8<T>(ldg16(pre_bias + (long long)n * C + col * 8), pb);
+    if (HB) unpack8<T>(ldg16(pre_bias + (long long)n * C + col * 8), pb);
   }
   const long long P = (HW + chunks - 1) / chunks;
   const long long p0 = chunk * P, p1 = p0 + P < HW ? p0 + P : HW;
@@ -282,41 +284,70 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const T* __restrict__ x, 
     unpack8<T>(raw, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float val = pre_bias ? to_f32(from_f32<T>(f[e] + pb[e])) : f[e];
+      const float val = HB ? to_f32(from_f32<T>(f[e] + pb[e])) : f[e];
       float t = fmaf(val, a[e], b[e]);
       if (silu) t = __fdividef(t, 1.f + __expf(-t));
       o[e] = t;
     }
     return pack8<T>(o);
   };
-  for (long long p = p0 + r; p < p1; p += (long long)kGnUnroll * R) {
-    uint4 raw[kGnUnroll];
+  for (long long p = p0 + r; p < p1; p += (long long)U * R) {
+    uint4 raw[U];
 #pragma unroll
-    for (int u = 0; u < kGnUnroll; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long long pp = p + (long long)u * R;
       raw[u] = pp < p1 ? *reinterpret_cast<const uint4*>(base + pp * C) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int u = 0; u < kGnUnroll; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long long pp = p + (long long)u * R;
       if (pp < p1) *reinterpret_cast<uint4*>(obase + pp * C) = transform(raw[u]);
     }
   }
 }
 
+template <typename T, int U, bool HB, int MAXT, int MINB>
+int launch_gn_v(const GnGeometry& g, const void* x, const void* pre_bias, const void* gamma, const void* beta, void* y, float* ws,
+                int N, long long HW, int C, int groups, float eps, int silu, cudaStream_t stream) {
+  const size_t smem = (size_t)2 * g.R * C * sizeof(float);
+  gn_stats_kernel<T, U, HB, MAXT, MINB><<<dim3(g.chunks_stats, N), g.threads, smem, stream>>>(
+      (const T*)x, (const T*)pre_bias, (float2*)ws, HW, C, groups, g.R, g.chunks_stats);
+  PAID_LAUNCH_CHECK("gn_stats_kernel");
+  gn_apply_kernel<T, U, HB, MAXT, MINB><<<dim3(g.chunks_apply, N), g.threads, 0, stream>>>(
+      (const T*)x, (const T*)pre_bias, (const float2*)ws, (const T*)gamma, (const T*)beta, (T*)y, HW, C, groups, g.R,
+      g.chunks_stats, g.chunks_apply, eps, silu);
+  PAID_LAUNCH_CHECK("gn_apply_kernel");
+  return PAID_OK;
+}
+
+// Two register / occupancy trade-offs of the same kernels (PAID_GN_VARIANT, default kGnDefaultVariant):
+//   0: 8 loads in flight per thread, ~100 registers, 16 warps per SM
+//   1: 4 loads in flight per thread, <= 64 registers, 32 warps per SM
+constexpr int kGnDefaultVariant = 0;
+
+template <typename T, bool HB>
+int launch_gn_hb(const void* x, const void* pre_bias, const void* gamma, const void* beta, void* y, float* ws, int N,
+                 long long HW, int C, int groups, float eps, int silu, cudaStream_t stream) {
+  const GnGeometry g = gn_geometry(N, HW, C);
+  const char* env = getenv("PAID_GN_VARIANT");
+  const int variant = env ? atoi(env) : kGnDefaultVariant;
+  const bool small = g.threads <= 256;
+#define PAID_GN_GO(U, MAXT, MINB) \
+  return launch_gn_v<T, U, HB, MAXT, MINB>(g, x, pre_bias, gamma, beta, y, ws, N, HW, C, groups, eps, silu, stream)
+  if (variant == 1) {
+    if (small) PAID_GN_GO(4, 256, 4);
+    PAID_GN_GO(4, 512, 2);
+  }
+  if (small) PAID_GN_GO(8, 256, 2);
+  PAID_GN_GO(8, 512, 1);
+#undef PAID_GN_GO
+}
+
 template <typename T>
 int launch_gn_t(const void* x, const void* pre_bias, const void* gamma, const void* beta, void* y, float* ws, int N,
                 long long HW, int C, int groups, float eps, int silu, cudaStream_t stream) {
-  const GnGeometry g = gn_geometry(N, HW, C);
-  const size_t smem = (size_t)2 * g.R * C * sizeof(float);
-  gn_stats_kernel<T><<<dim3(g.chunks_stats, N), g.threads, smem, stream>>>((const T*)x, (const T*)pre_bias, (float2*)ws, HW, C,
-                                                                          groups, g.R, g.chunks_stats);
-  PAID_LAUNCH_CHECK("gn_stats_kernel");
-  gn_apply_kernel<T><<<dim3(g.chunks_apply, N), g.threads, 0, stream>>>((const T*)x, (const T*)pre_bias, (const float2*)ws,
-                                                                       (const T*)gamma, (const T*)beta, (T*)y, HW, C, groups,
-                                                                       g.R, g.chunks_stats, g.chunks_apply, eps, silu);
-  PAID_LAUNCH_CHECK("gn_apply_kernel");
-  return PAID_OK;
+  return pre_bias ? launch_gn_hb<T, true>(x, pre_bias, gamma, beta, y, ws, N, HW, C, groups, eps, silu, stream)
+                  : launch_gn_hb<T, false>(x, pre_bias, gamma, beta, y, ws, N, HW, C, groups, eps, silu, stream);
 }
 
 }  // namespace

@@ -439,10 +439,12 @@ def test_add_layer_norm_against_torch(cabi):
         assert torch.equal(h1, h2) and torch.equal(x1, x2)
 
 
-def test_group_norm_nhwc_against_torch(cabi):
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_group_norm_nhwc_against_torch(cabi, variant, monkeypatch):
     """paid_group_norm_nhwc (+ SiLU, + per-(n,c) pre-bias) vs torch GroupNorm in fp32 on every channel width the
     SD1.5 / SDXL UNets normalise (incl. the skip concatenations), odd spatial sizes, a large mean offset (variance by
     partial (mean, M2) merging, not E[x^2] - E[x]^2 over the whole group), and bit-exact repeatability."""
+    monkeypatch.setenv("PAID_GN_VARIANT", variant)      # both register / occupancy variants of the kernels
     torch.manual_seed(6)
     F = torch.nn.functional
     shapes = [(7, 320, 128, 128), (3, 640, 64, 64), (2, 960, 32, 32), (2, 1280, 32, 32), (1, 1920, 16, 16), (2, 2560, 8, 8),
