@@ -320,17 +320,20 @@ int launch_gn_v(const GnGeometry& g, const void* x, const void* pre_bias, const 
   return PAID_OK;
 }
 
-// Two register / occupancy trade-offs of the same kernels (PAID_GN_VARIANT, default kGnDefaultVariant):
+// Two register / occupancy trade-offs of the same kernels (PAID_GN_VARIANT forces one):
 //   0: 8 loads in flight per thread, ~100 registers, 16 warps per SM
 //   1: 4 loads in flight per thread, <= 64 registers, 32 warps per SM
-constexpr int kGnDefaultVariant = 0;
+// Measured on B200 (tools/bench_glue.py, L2 flushed, N = 7, profiles/r1_glue_bench.jsonl): variant 1 is 8-17 % faster on
+// the 64x64 and 128x128 feature maps (many pixels per CTA: occupancy hides the latency), variant 0 is 10-16 % faster on
+// the 32x32 maps (few pixels per CTA: everything a thread will ever load is in flight at once).
+__host__ inline int gn_default_variant(long long HW) { return HW >= 4096 ? 1 : 0; }
 
 template <typename T, bool HB>
 int launch_gn_hb(const void* x, const void* pre_bias, const void* gamma, const void* beta, void* y, float* ws, int N,
                  long long HW, int C, int groups, float eps, int silu, cudaStream_t stream) {
   const GnGeometry g = gn_geometry(N, HW, C);
   const char* env = getenv("PAID_GN_VARIANT");
-  const int variant = env ? atoi(env) : kGnDefaultVariant;
+  const int variant = env ? atoi(env) : gn_default_variant(HW);
   const bool small = g.threads <= 256;
 #define PAID_GN_GO(U, MAXT, MINB) \
   return launch_gn_v<T, U, HB, MAXT, MINB>(g, x, pre_bias, gamma, beta, y, ws, N, HW, C, groups, eps, silu, stream)
