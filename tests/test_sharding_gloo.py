@@ -59,3 +59,61 @@ def test_two_rank_endpoint_broadcast():
     [p.join(30) for p in procs]
     assert [r for r, _ in res] == [0, 1]
     assert all(e < 1e-12 for _, e in res), res
+
+
+def _ip_worker(rank, world, port, q):
+    """Frame-sharded IP-Adapter call: the PRODUCT's endpoint exchange (_InterpolatedIPAttnProcessor._endpoints: rows of
+    the local K/V on the owner ranks, broadcast over the process group) feeds the oracle's per-rank math."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from attention_interpolation_diffusion_b200 import (OuterInterpolatedIPAttnProcessor, PaidIPAdapterAttnProcessor,
+                                                            ScaleControlIPAttnProcessor)
+        N, S, C, h, Cc, L, T = 6, 20, 64, 2, 48, 9, 4
+        dt = torch.float64
+        w = O.make_layer(C, Cc, h, 5, dt)
+        x, ctx = O.make_inputs(N, S, C, L, Cc, 5, dt)
+        ip, wk_ip, wv_ip = O.make_ip(N, T, C, Cc, 5, dt)
+        coef = O.coefficients(N, 3, 3).double()
+        scale = (C // h) ** -0.5
+        sh = FrameShard(rank, world, N)
+        ipa = PaidIPAdapterAttnProcessor(C, Cc, num_tokens=(T,), scale=0.6)
+        ql, kl, vl, kipl, vipl = O._ip_parts(sh.local(x), sh.local(ctx), sh.local(ip), w, wk_ip, wv_ip)
+        cl = sh.local(coef)
+        errs = []
+        # outer-IP: text and image-token endpoints both exchanged
+        proc = OuterInterpolatedIPAttnProcessor(size=N, is_fused=True, alpha=3, beta=3, ip_attn=ipa)
+        proc.shard = sh
+        et, ei = proc._endpoints(kl, vl), proc._endpoints(kipl, vipl)
+        assert et["begin_frame"] == (0 if rank == sh.begin_owner else -1)
+        assert et["end_frame"] == (sh.local_frames - 1 if rank == sh.end_owner else -1)
+        hid = O._direct_core(ql, kl, vl, tuple(et["kv_ext"]), cl, O.MODE_OUTER, True, scale, h)
+        hid = hid + 0.6 * O._direct_core(ql, kipl, vipl, tuple(ei["kv_ext"]), cl, O.MODE_OUTER, True, scale, h)
+        full = O.forward_ip_outer(x, ctx, ip, w, wk_ip, wv_ip, coef, True, 0.6)
+        errs.append(float((hid @ w.wo.T + w.bo - sh.local(full)).abs().max()))
+        # scale control: only the END frame's image-token K/V travel
+        proc = ScaleControlIPAttnProcessor(size=N, is_fused=True, alpha=3, beta=3, ip_attn=ipa)
+        proc.shard = sh
+        kv = proc._endpoints(kipl[-1:], vipl[-1:], need_begin=False)["kv_ext"]
+        n = sh.local_frames
+        hid = O._direct_core(ql, kl, vl, tuple(et["kv_ext"]), cl, O.MODE_OUTER, True, scale, h)
+        hid = hid + cl.reshape(n, 1, 1) * O._direct_core(ql, kv[2:3].expand(n, -1, -1), kv[3:4].expand(n, -1, -1), None, None,
+                                                         O.MODE_PLAIN, False, scale, h)
+        full = O.forward_ip_scale_control(x, ctx, ip, w, wk_ip, wv_ip, coef, True, True)
+        errs.append(float((hid @ w.wo.T + w.bo - sh.local(full)).abs().max()))
+        q.put((rank, max(errs)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_ip_adapter_endpoint_exchange():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ip_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=100) for _ in procs)
+    [p.join(30) for p in procs]
+    assert [r for r, _ in res] == [0, 1]
+    assert all(e < 1e-12 for _, e in res), res
