@@ -17,6 +17,8 @@ the checkpoint's scheduler).
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional
 
 import torch
@@ -177,8 +179,10 @@ class InterpolationPipeline:
         self.scheduler.set_timesteps(num_inference_steps)
         warmup_steps = int(num_inference_steps * warmup_ratio)
         latents = latents * self.scheduler.init_noise_sigma
+        # multi-rank shards launch eagerly: the per-layer NCCL broadcast inside a captured forward is untested on this
+        # stack (PAID_SHARD_GRAPHS=1 opts in, every rank captures the same sequence of collectives)
         graphs = (self.use_cuda_graphs and latents.is_cuda and
-                  (self.shard is None or self.shard.world_size == 1))
+                  (self.shard is None or self.shard.world_size == 1 or os.environ.get("PAID_SHARD_GRAPHS") == "1"))
         for i, t in enumerate(self.scheduler.timesteps.tolist()):
             model_in = self.scheduler.scale_model_input(latents, t)
             noise_text = self._forward(i < warmup_steps, coef, model_in, t, cond, added_cond, graphs)
