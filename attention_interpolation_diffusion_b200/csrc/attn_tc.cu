@@ -60,8 +60,12 @@ template <int QT, int DT, int SP = 1> struct Shape {
   static constexpr int kThreads = 128 * (1 + QT * SP);   // warpgroup 0: TMA + MMA (+2 idle warps); the others: softmax
   static constexpr int kCtasPerSm = (QT == 2 || DT > 1) ? 1 : 2;
   // setmaxnreg split of the register file among the CTA's warpgroups (per-CTA budget 64K / kCtasPerSm)
+  // setmaxnreg.inc draws from the CTA's OWN launch allocation (kThreads x launch registers), so the split must satisfy
+  // 128 kRegsControl + (kThreads - 128) kRegsSoftmax <= kThreads x launch registers, or the .inc never returns.
+  // SP = 2 launches with 80 registers: 384 x 80 = 30720 >= 128 x 56 + 256 x 88 = 29696 (no spills at 88).  The first
+  // GPU try used 56 / 96 = 31744 and tripped the watchdog at exactly that point; 56 / 88 has NOT run on a GPU yet.
   static constexpr int kRegsControl = 56;
-  static constexpr int kRegsSoftmax = SP == 2 ? 96 : (QT == 2 ? 224 : 200);
+  static constexpr int kRegsSoftmax = SP == 2 ? 88 : (QT == 2 ? 224 : 200);
   static constexpr uint32_t kTmemCols = DT == 1 ? 256 * QT : 512;
   static constexpr uint32_t kTmemAcc = 128 * QT;     // S buffers first (2 x 64 columns per tile), accumulators after
   static constexpr uint32_t kAccTile = 128 * DT;     // accumulator columns per Q tile: 2 streams x 64 DT
@@ -236,7 +240,8 @@ __device__ __forceinline__ void softmax_split_rows(Barriers* bar, float* xch, ui
   const float cf[2] = {seg.a_active ? os * plan.wA / lt[0] : 0.f, seg.b_active ? os * plan.wB / lt[1] : 0.f};
   const bool active[2] = {seg.a_active, seg.b_active};
   const int row = row0 + r;
-  if (half * 32 >= a.head_dim) return;   // padded columns (head_dim <= 32): nothing to store
+  if (half * 32 >= a.head_dim) return;   // padded columns (head_dim <= 32): nothing to store (the caller's final
+                                         // __syncthreads is reached after this function returns)
   T* dst = (T*)a.out + ((long long)n * a.S + row) * (a.heads * a.head_dim) + head * a.head_dim + half * 32;
   float acc[32];
 #pragma unroll
