@@ -66,7 +66,9 @@ NATIVE_GLUE = os.environ.get("PAID_NATIVE_GLUE", "1") != "0"
 def _native(x: torch.Tensor) -> bool:
     """Half-precision CUDA tensors take libpaid_attn's fused glue kernels; anything else (the CPU tests that host the
     oracle processors in this harness) takes the plain PyTorch composition of the same ops."""
-    return NATIVE_GLUE and x.is_cuda and x.dtype in (torch.float16, torch.bfloat16)
+    if x.is_cuda and NATIVE_GLUE and x.dtype not in (torch.float16, torch.bfloat16):
+        raise TypeError(f"the CUDA path computes in fp16 / bf16 (got {x.dtype}); there is no fp32 GPU path")
+    return NATIVE_GLUE and x.is_cuda
 
 
 def group_norm(gn: nn.GroupNorm, x: torch.Tensor, silu: bool = False, pre_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
