@@ -48,3 +48,36 @@ def test_scheduler_and_slerp():
     import paid_oracle as O
     a, b = torch.randn(1, 4, 8, 8), torch.randn(1, 4, 8, 8)
     assert torch.allclose(slerp(a, b, 0.3), O.slerp(a, b, 0.3), atol=1e-6)
+
+
+def test_oracle_processor_hosts_the_reference_semantics_in_the_harness():
+    """OracleAttnProcessor (test infrastructure for the end-to-end comparison, oracle/gen_e2e_golden.py): one layer equals
+    the oracle's forward_direct, and a whole CPU denoise of the tiny UNet through the pipeline runs with it (activate /
+    deactivate / set_coefs driven by the pipeline exactly as for the product processors)."""
+    import paid_oracle as O
+    from oracle_processor import OracleAttnProcessor
+    from attention_interpolation_diffusion_b200.attention import Attention
+    from attention_interpolation_diffusion_b200.unet_harness import build_unet
+    torch.manual_seed(3)
+    attn = Attention(64, 48, 2, 32)
+    x, ctx = torch.randn(4, 20, 64), torch.randn(4, 9, 48)
+    w = O.LayerWeights(attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, attn.to_out[0].weight, attn.to_out[0].bias, 2)
+    for mode in (O.MODE_OUTER, O.MODE_INNER):
+        proc = OracleAttnProcessor(mode, True, size=4)
+        proc.set_coefs(torch.tensor([0.0, 0.3, 0.8, 1.0]))
+        attn.set_processor(proc)
+        with torch.no_grad():
+            y = attn(x, encoder_hidden_states=ctx)
+            assert torch.allclose(y, O.forward_direct(x, ctx, w, proc.coef, mode, True), atol=1e-5)
+            proc.deactivate()
+            assert torch.allclose(attn(x, encoder_hidden_states=ctx), O.forward_direct(x, ctx, w, None, O.MODE_PLAIN, False), atol=1e-5)
+    net = build_unet("tiny", "cpu", torch.float32, seed=2)
+    pipe = InterpolationPipeline(net, use_cuda_graphs=False)
+    net.set_attn_processor({n: OracleAttnProcessor(O.MODE_OUTER, True, 3, 0.5) for n in net.attn_processors})
+    g = torch.Generator("cpu").manual_seed(4)
+    r = lambda *s: torch.randn(*s, generator=g)
+    out = pipe.interpolate(latent_start=r(1, 4, 16, 16), latent_end=r(1, 4, 16, 16), embeds_start=r(1, 77, 96),
+                           embeds_end=r(1, 77, 96), negative_embeds=r(1, 77, 96), pooled_start=r(1, 1280),
+                           pooled_end=r(1, 1280), pooled_negative=r(1, 1280), size=3, coef=torch.tensor([0.0, 0.5, 1.0]),
+                           num_inference_steps=4)
+    assert out.shape == (3, 4, 16, 16) and torch.isfinite(out).all()

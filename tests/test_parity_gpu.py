@@ -532,3 +532,31 @@ def test_ip_pipeline_and_frame_shard(cabi, early):
         assert torch.isfinite(outs[name]).all()
     check(outs["graphs"], outs["eager"], (early, "graph replay vs eager"), rel=1e-3)
     check(outs["shard"], outs["eager"], (early, "world-size-1 shard vs unsharded"), rel=2e-3)
+
+
+def test_e2e_sd15_c1_drift(cabi, record_property):
+    """BASELINE configs[0] end to end: SD1.5 64x64 latent, 3 frames, 10 steps.  The CUDA pipeline
+    in fp16 against the final latents of the same loop run on the CPU in fp32 with the reference's processor semantics
+    (tests/golden/e2e_sd15_c1.npz, oracle/gen_e2e_golden.py), same CPU-initialised weights.  Ten chained UNet passes
+    amplify rounding differences, so the drift is REPORTED (printed, recorded as a test property, SURVEY 8c: "reported, not
+    gated"); the gate is only that the run completes with finite latents of the right shape."""
+    import os
+    import numpy as np
+    from golden_util import GOLDEN as GOLDEN_DIR
+    import gen_e2e_golden as G
+    from attention_interpolation_diffusion_b200.pipeline import InterpolationPipeline
+    path = os.path.join(GOLDEN_DIR, "e2e_sd15_c1.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/e2e_sd15_c1.npz has not been generated")
+    ref = torch.from_numpy(np.load(path)["latents"])
+    net = G.c1_unet_cpu().half().cuda().to(memory_format=torch.channels_last)
+    pipe = InterpolationPipeline(net, use_cuda_graphs=False)
+    pipe.load_aid(t=G.C1["t"], is_fused=True, atype="fused_outer", size=G.C1["frames"])
+    inputs = {k: v.cuda() for k, v in G.c1_inputs(torch.float16).items()}
+    out = pipe.interpolate(**inputs, **G.c1_call_kwargs()).float().cpu()
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    drift = float((out - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    cos = float(torch.nn.functional.cosine_similarity(out.flatten(), ref.flatten(), dim=0))
+    record_property("e2e_c1_rel_rms_drift", drift)
+    record_property("e2e_c1_cosine", cos)
+    print(f"\ne2e C1 (SD1.5, 3 frames, 10 steps): rel-RMS drift fp16 CUDA vs fp32 CPU reference semantics = {drift:.3e}, cosine = {cos:.6f}")
