@@ -266,6 +266,18 @@ class InterpolationPipeline:
                              self._added(n, pooled_u, lat.device, lat.dtype), coef, num_inference_steps, g, warmup_ratio)
 
     @torch.no_grad()
+    def interpolate_candidates(self, ts, latent_start, latent_end, embeds_start, embeds_end, negative_embeds, **kw):
+        """Frames for several interpolation parameters ``ts`` in ONE batch ``[start, t_1, ..., t_K, end]``.  Interior
+        frames interact with the rest of the batch only through the endpoint K/V, so frame i equals the middle frame
+        of the reference's 3-frame ``interpolate_single(t_i)`` (SURVEY.md section 4 property 2): the K sequential
+        denoises of the reference's exploration loop (prior.py:119-199 runs one per candidate) become one sharded
+        batch.  The candidate SELECTION of that loop (CLIP distances, Beta fit) stays with the caller."""
+        ts = [float(t) for t in ts]
+        assert all(0 < t < 1 for t in ts), "t must be between 0 and 1"
+        return self.interpolate(latent_start, latent_end, embeds_start, embeds_end, negative_embeds, size=len(ts) + 2,
+                                coef=torch.tensor([0.0, *ts, 1.0]), **kw)
+
+    @torch.no_grad()
     def interpolate_single(self, it: float, latent_start, latent_end, embeds_start, embeds_end, negative_embeds,
                            guide_embeds=None, warmup_ratio: float = 0.5, num_inference_steps: int = 50,
                            guidance_scale: Optional[float] = None, **pooled):

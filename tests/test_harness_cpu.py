@@ -81,3 +81,27 @@ def test_oracle_processor_hosts_the_reference_semantics_in_the_harness():
                            pooled_end=r(1, 1280), pooled_negative=r(1, 1280), size=3, coef=torch.tensor([0.0, 0.5, 1.0]),
                            num_inference_steps=4)
     assert out.shape == (3, 4, 16, 16) and torch.isfinite(out).all()
+
+
+def test_candidates_in_one_batch_equal_sequential_three_frame_runs():
+    """Pipeline-level form of property 2, with the reference's processor semantics on the CPU:
+    denoising K candidate t's in one batch [start, t_1..t_K, end] gives, frame by frame, the middle frame of the
+    reference's sequential 3-frame interpolate_single(t_i) runs (prior.py:119-199 runs them one after the other)."""
+    import paid_oracle as O
+    from oracle_processor import OracleAttnProcessor
+    from attention_interpolation_diffusion_b200.unet_harness import build_unet
+    net = build_unet("tiny", "cpu", torch.float64, seed=6)
+    pipe = InterpolationPipeline(net, use_cuda_graphs=False)
+    net.set_attn_processor({n: OracleAttnProcessor(O.MODE_OUTER, True, 3, 0.5) for n in net.attn_processors})
+    g = torch.Generator("cpu").manual_seed(8)
+    r = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    args = dict(latent_start=r(1, 4, 16, 16), latent_end=r(1, 4, 16, 16), embeds_start=r(1, 77, 96), embeds_end=r(1, 77, 96),
+                negative_embeds=r(1, 77, 96), pooled_start=r(1, 1280), pooled_end=r(1, 1280), pooled_negative=r(1, 1280),
+                num_inference_steps=4)
+    ts = [0.25, 0.6, 0.8]
+    batch = pipe.interpolate_candidates(ts, **args)
+    assert batch.shape == (5, 4, 16, 16)
+    for i, t in enumerate(ts):
+        single = pipe.interpolate_single(t, **args)
+        assert torch.allclose(batch[i + 1], single[1], atol=1e-9), (t, float((batch[i + 1] - single[1]).abs().max()))
+        assert torch.allclose(batch[0], single[0], atol=1e-9) and torch.allclose(batch[-1], single[2], atol=1e-9)
