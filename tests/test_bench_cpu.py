@@ -1,0 +1,35 @@
+"""CPU: the parts of bench.py that do not need a GPU -- the reference arm's JSON line (on the tiny geometry so it takes
+seconds) and the committed ncu traffic table covering every attention-layer class of the headline workload."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--model", "tiny", "--frames", "3",
+                          "--steps", "1", "--warmup", "0", "--denoise-steps", "4"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == os.cpu_count()
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
+
+
+def test_committed_ncu_traffic_covers_the_headline_workload():
+    sys.path.insert(0, ROOT)
+    import bench
+    from attention_interpolation_diffusion_b200.unet_harness import CONFIGS, UNetHarness
+    with torch.device("meta"):
+        net = UNetHarness(CONFIGS["sdxl"])
+    traffic, alg, how = bench.attention_traffic(net, 7, 25, 75)
+    assert traffic is not None and alg is not None, how
+    assert 0.3 * alg < traffic < 3 * alg, (traffic, alg)      # DRAM traffic of the same order as the algorithmic bytes
