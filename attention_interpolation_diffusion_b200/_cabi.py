@@ -20,11 +20,12 @@ PAID_OK, PAID_EINVAL, PAID_EUNSUPPORTED, PAID_ECUDA, PAID_EWORKSPACE = 0, -1, -2
 PAID_F16, PAID_BF16 = 0, 1
 PAID_PLAIN, PAID_OUTER, PAID_INNER = 0, 1, 2
 FLAG_GENERIC_KERNELS = 1
+FLAG_ONE_WARPGROUP = 2
 MODES = {"plain": PAID_PLAIN, "outer": PAID_OUTER, "inner": PAID_INNER}
 
 EXPORTS = [
     "paid_attn_abi_version", "paid_attn_workspace_bytes", "paid_attn_core_workspace_bytes", "paid_attn_forward",
-    "paid_attn_core", "paid_attn_project_endpoints", "paid_linear", "paid_attn_last_error",
+    "paid_attn_core", "paid_attn_project_endpoints", "paid_attn_project_kv", "paid_linear", "paid_attn_last_error",
     "paid_attn_launch_count", "paid_attn_last_kernel", "paid_attn_profile_enable", "paid_attn_profile_read",
     "paid_geglu", "paid_add_layer_norm", "paid_group_norm_nhwc", "paid_group_norm_workspace_bytes",
     "paid_residual_bias_add",
@@ -41,6 +42,8 @@ class PaidAttnParams(C.Structure):
         ("x", C.c_void_p), ("ctx", C.c_void_p), ("wq", C.c_void_p), ("wk", C.c_void_p), ("wv", C.c_void_p),
         ("wo", C.c_void_p), ("bo", C.c_void_p), ("coef", C.c_void_p), ("kv_ext", C.c_void_p),
         ("y", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
+        ("k_pre", C.c_void_p), ("v_pre", C.c_void_p), ("kv_pre_broadcast", C.c_int32), ("reserved0", C.c_int32),
+        ("kv_ext_ready_event", C.c_void_p),
     ]
 
 
@@ -81,6 +84,8 @@ def load_library() -> C.CDLL:
     lib.paid_attn_core.argtypes = [C.POINTER(PaidCoreParams), C.c_void_p]
     lib.paid_attn_project_endpoints.restype = C.c_int
     lib.paid_attn_project_endpoints.argtypes = [C.POINTER(PaidAttnParams), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.paid_attn_project_kv.restype = C.c_int
+    lib.paid_attn_project_kv.argtypes = [C.POINTER(PaidAttnParams), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.paid_linear.restype = C.c_int
     lib.paid_linear.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                 C.c_int32, C.c_uint32, C.c_void_p]
@@ -102,7 +107,7 @@ def load_library() -> C.CDLL:
     lib.paid_attn_profile_enable.argtypes = [C.c_int]
     lib.paid_attn_profile_read.restype = C.c_int
     lib.paid_attn_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.c_int]
-    if lib.paid_attn_abi_version() != 1:
+    if lib.paid_attn_abi_version() != 2:
         raise RuntimeError("libpaid_attn.so ABI version mismatch")
     _lib = lib
     return lib
@@ -194,18 +199,28 @@ def make_params(x, ctx, wq, wk, wv, wo, bo, coef, heads: int, mode: int, fused: 
 
 
 def attn_forward(x, ctx, wq, wk, wv, wo, bo, coef, heads: int, mode: int, fused: bool, scale=None,
-                 begin_frame=None, end_frame=None, kv_ext=None, flags: int = 0, out=None) -> torch.Tensor:
+                 begin_frame=None, end_frame=None, kv_ext=None, flags: int = 0, out=None, k_pre=None, v_pre=None,
+                 kv_pre_broadcast: bool = False, kv_ext_ready=None) -> torch.Tensor:
     """One processor call through ``paid_attn_forward``.  Tensors: x (N,S,C), ctx None|(N,L,Cc), weights as in
-    nn.Linear, coef fp32 (N,) on the device (None for plain mode)."""
+    nn.Linear, coef fp32 (N,) on the device (None for plain mode).  ``k_pre`` / ``v_pre``: K / V of the context projected
+    earlier with ``project_kv`` ((N,L,C), or (1,L,C) with ``kv_pre_broadcast``); ``kv_ext_ready``: a ``torch.cuda.Event``
+    the stream waits for before the attention core (the endpoint K/V in ``kv_ext`` arrive on another stream)."""
     lib = load_library()
-    _dev_check(x, ctx, wq, wk, wv, wo, bo, coef, kv_ext)
-    for t in (ctx, wq, wk, wv, wo, bo, kv_ext):
+    _dev_check(x, ctx, wq, wk, wv, wo, bo, coef, kv_ext, k_pre, v_pre)
+    for t in (ctx, wq, wk, wv, wo, bo, kv_ext, k_pre, v_pre):
         if t is not None and t.dtype != x.dtype:
             raise RuntimeError("all tensors of a call must share one dtype")
     if coef is not None and coef.dtype != torch.float32:
         raise RuntimeError("coef must be fp32")
     y = torch.empty_like(x) if out is None else out
     p = make_params(x, ctx, wq, wk, wv, wo, bo, coef, heads, mode, fused, scale, begin_frame, end_frame, kv_ext, flags, y)
+    if k_pre is not None:
+        if ctx is None and k_pre.shape[1] != x.shape[1]:
+            raise RuntimeError("k_pre of a self-attention call must have S tokens")
+        p.L = k_pre.shape[1]
+        p.k_pre, p.v_pre, p.kv_pre_broadcast = k_pre.data_ptr(), v_pre.data_ptr(), int(bool(kv_pre_broadcast))
+    if kv_ext_ready is not None:
+        p.kv_ext_ready_event = kv_ext_ready.cuda_event
     need = lib.paid_attn_workspace_bytes(C.byref(p))
     if need == 0:
         raise RuntimeError(f"paid_attn_workspace_bytes rejected the parameters: {last_error()}")
@@ -224,12 +239,21 @@ def project_endpoints(x, ctx, wk, wv, heads: int, local_frame: int, k_out: torch
            "paid_attn_project_endpoints")
 
 
-def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
+def project_kv(x, ctx, wk, wv, heads: int, k_out: torch.Tensor, v_out: torch.Tensor, flags: int = 0):
+    """K / V of every frame of the context (``paid_attn_project_kv``) into k_out / v_out (N,L,C)."""
     lib = load_library()
-    _dev_check(x, w, bias)
+    _dev_check(x, ctx, wk, wv, k_out, v_out)
+    p = make_params(x, ctx, None, wk, wv, None, None, None, heads, PAID_PLAIN, False, flags=flags)
+    _check(lib.paid_attn_project_kv(C.byref(p), k_out.data_ptr(), v_out.data_ptr(), _stream(x)), "paid_attn_project_kv")
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, flags: int = 0,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = load_library()
+    _dev_check(x, w, bias, out)
     K = x.shape[-1]
     M = x.numel() // K
-    y = torch.empty(*x.shape[:-1], w.shape[0], dtype=x.dtype, device=x.device)
+    y = torch.empty(*x.shape[:-1], w.shape[0], dtype=x.dtype, device=x.device) if out is None else out
     _check(lib.paid_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), M, w.shape[0], K, _dtype_code(x),
                            flags, _stream(x)), "paid_linear")
     return y

@@ -15,16 +15,65 @@ from torch import nn
 from . import _cabi
 
 
+def static_kv(attn, encoder_hidden_states):
+    """Per-sequence K/V cache of a cross-attention layer.  The prompt embeddings do not change over the denoising steps
+    (pipeline_interpolated_sdxl.py:2232-2345 feeds the same ``prompt_embeds`` to every UNet call), so the step loop
+    projects them once per sequence (``InterpolationPipeline._refresh_static_kv`` -> ``project_static`` of the layer's
+    processor) into ``attn.paid_kv[tag]`` for tag = "cond" / "uncond", and names the running pass in
+    ``attn.paid_kv_tag[0]``.  Returns that entry, or None (no cache attached, self-attention, other pass): then the
+    call projects K / V itself, as the reference does on every call."""
+    store = getattr(attn, "paid_kv", None)
+    if store is None or encoder_hidden_states is None:
+        return None
+    return store.get(attn.paid_kv_tag[0])
+
+
+def _static_buffer(entry: dict, name: str, shape, like: torch.Tensor) -> torch.Tensor:
+    """Persistent buffer of a cache entry (re-used across sequences: captured CUDA graphs hold its address)."""
+    t = entry.get(name)
+    if t is None or tuple(t.shape) != tuple(shape) or t.dtype != like.dtype or t.device != like.device:
+        t = entry[name] = torch.empty(*shape, dtype=like.dtype, device=like.device)
+        entry["reallocated"] = True
+    return t
+
+
+def project_text_static(attn, ctx: torch.Tensor, uniform: bool, entry: dict, endpoints: Optional[torch.Tensor] = None,
+                        flags: int = 0, prefix: str = "", wk=None, wv=None):
+    """K / V of a step-invariant context ``ctx`` (n, L, Cc) into ``entry`` (keys prefix + "k" / "v"): one (1, L, C) pair
+    when every frame carries the same context (``uniform``, the unconditional pass), else per frame.  ``endpoints``
+    (2, L, Cc): the two endpoint prompts of a frame-sharded sequence -> prefix + "kv_ext" (4, L, C), projected locally."""
+    wk = attn.to_k.weight if wk is None else wk
+    wv = attn.to_v.weight if wv is None else wv
+    C = wk.shape[0]
+    src = (ctx[:1] if uniform else ctx).contiguous()
+    n, L = src.shape[0], src.shape[1]
+    probe = src.new_empty(n, 1, C)      # only its shape / dtype are read
+    k = _static_buffer(entry, prefix + "k", (n, L, C), src)
+    v = _static_buffer(entry, prefix + "v", (n, L, C), src)
+    _cabi.project_kv(probe, src, wk, wv, attn.heads, k, v, flags)
+    entry[prefix + "broadcast"] = bool(uniform)
+    if endpoints is not None:
+        kv = _static_buffer(entry, prefix + "kv_ext", (4, L, C), src)
+        ends = endpoints.contiguous()
+        for f in range(2):
+            _cabi.project_endpoints(src.new_empty(2, 1, C), ends, wk, wv, attn.heads, f, kv[2 * f], kv[2 * f + 1], flags)
+
+
 class PaidAttnProcessor:
     """Stock (non-interpolated) attention through the PLAIN mode of libpaid_attn --
     the role ``AttnProcessor2_0`` plays in the reference (``original_attn``,
     pipeline_interpolated_sdxl.py:1076)."""
 
+    def project_static(self, attn, ctx, uniform, entry, endpoints=None):
+        project_text_static(attn, ctx, uniform, entry, None)
+
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
         check_unet_preconditions(attn, hidden_states, attention_mask)
+        st = static_kv(attn, encoder_hidden_states) or {}
         return _cabi.attn_forward(
             hidden_states, encoder_hidden_states, attn.to_q.weight, attn.to_k.weight, attn.to_v.weight,
-            attn.to_out[0].weight, attn.to_out[0].bias, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale)
+            attn.to_out[0].weight, attn.to_out[0].bias, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale,
+            k_pre=st.get("k"), v_pre=st.get("v"), kv_pre_broadcast=st.get("broadcast", False))
 
 
 def split_ip_states(encoder_hidden_states, num_tokens, batch):
@@ -57,16 +106,25 @@ class PaidIPAdapterAttnProcessor(nn.Module):
         self.to_k_ip = nn.ModuleList([nn.Linear(cross_attention_dim, hidden_size, bias=False)])
         self.to_v_ip = nn.ModuleList([nn.Linear(cross_attention_dim, hidden_size, bias=False)])
 
+    def project_static(self, attn, ctx, uniform, entry, endpoints=None):
+        text, ip = split_ip_states(ctx, self.num_tokens, ctx.shape[0])
+        project_text_static(attn, text, uniform, entry)
+        project_text_static(attn, ip, uniform, entry, prefix="ip_", wk=self.to_k_ip[0].weight, wv=self.to_v_ip[0].weight)
+
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
         check_unet_preconditions(attn, hidden_states, attention_mask)
         x = hidden_states
-        text, ip = split_ip_states(encoder_hidden_states, self.num_tokens, x.shape[0])
+        st = static_kv(attn, encoder_hidden_states)
         q = _cabi.linear(x, attn.to_q.weight)
-        hid = _cabi.attn_core(q, _cabi.linear(text, attn.to_k.weight), _cabi.linear(text, attn.to_v.weight), None,
-                              attn.heads, _cabi.PAID_PLAIN, False, attn.scale)
-        _cabi.attn_core(q, _cabi.linear(ip, self.to_k_ip[0].weight), _cabi.linear(ip, self.to_v_ip[0].weight), None,
-                        attn.heads, _cabi.PAID_PLAIN, False, attn.scale, out=hid, accumulate=True,
-                        out_scale=float(self.scale[0]))
+        if st is not None:
+            k, v, kip, vip, bc = st["k"], st["v"], st["ip_k"], st["ip_v"], st["broadcast"]
+        else:
+            text, ip = split_ip_states(encoder_hidden_states, self.num_tokens, x.shape[0])
+            k, v = _cabi.linear(text, attn.to_k.weight), _cabi.linear(text, attn.to_v.weight)
+            kip, vip, bc = _cabi.linear(ip, self.to_k_ip[0].weight), _cabi.linear(ip, self.to_v_ip[0].weight), False
+        hid = _cabi.attn_core(q, k, v, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale, kv_broadcast=bc)
+        _cabi.attn_core(q, kip, vip, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale, out=hid, accumulate=True,
+                        out_scale=float(self.scale[0]), kv_broadcast=bc)
         return _cabi.linear(hid, attn.to_out[0].weight, attn.to_out[0].bias)
 
 

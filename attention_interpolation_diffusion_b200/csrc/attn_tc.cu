@@ -49,23 +49,17 @@ constexpr int KV_BYTES = BN * D * 2;   //  8 KB: one 64-column chunk of a K or V
 // swizzled shared-memory tile per operand: Q K^T accumulates over the chunks (K dimension), P V is issued once per
 // chunk (N = 64 each) into adjacent accumulator columns, so every MMA and descriptor is the head_dim-64 one.
 // DT > 1 needs 128 + 2 * 64 DT > 256 TMEM columns: one CTA per SM, QT = 1 only.
-// SP = threads per query row in the softmax (experimental, PAID_ATTN_SPLIT=1): SP = 2 gives every Q tile two softmax
-// warpgroups, each owning 32 of a score tile's 64 columns (row maxima and denominators exchanged through shared
-// memory), i.e. four softmax warps per scheduler with half the registers each instead of two.
-template <int QT, int DT, int SP = 1> struct Shape {
+template <int QT, int DT> struct Shape {
   static_assert(DT == 1 || QT == 1, "wide heads run with one Q tile per CTA");
-  static_assert(SP == 1 || (SP == 2 && QT == 1 && DT == 1), "the split-row softmax exists for QT = 1, head_dim <= 64");
   static constexpr int kStages = DT == 3 ? 3 : (QT == 2 ? ST : 5);   // K/V ring stages (227 KB per SM)
-  static constexpr int kSmemBytes = 1024 + QT * DT * Q_BYTES + kStages * 2 * DT * KV_BYTES + 512 + (SP == 2 ? 4096 : 0);
-  static constexpr int kThreads = 128 * (1 + QT * SP);   // warpgroup 0: TMA + MMA (+2 idle warps); the others: softmax
+  static constexpr int kSmemBytes = 1024 + QT * DT * Q_BYTES + kStages * 2 * DT * KV_BYTES + 512;
+  static constexpr int kThreads = 128 * (1 + QT);   // warpgroup 0: TMA + MMA (+2 idle warps); the others: softmax
   static constexpr int kCtasPerSm = (QT == 2 || DT > 1) ? 1 : 2;
   // setmaxnreg split of the register file among the CTA's warpgroups (per-CTA budget 64K / kCtasPerSm)
   // setmaxnreg.inc draws from the CTA's OWN launch allocation (kThreads x launch registers), so the split must satisfy
   // 128 kRegsControl + (kThreads - 128) kRegsSoftmax <= kThreads x launch registers, or the .inc never returns.
-  // SP = 2 launches with 80 registers: 384 x 80 = 30720 >= 128 x 56 + 256 x 88 = 29696 (no spills at 88).  The first
-  // GPU try used 56 / 96 = 31744 and tripped the watchdog at exactly that point; 56 / 88 has NOT run on a GPU yet.
   static constexpr int kRegsControl = 56;
-  static constexpr int kRegsSoftmax = SP == 2 ? 88 : (QT == 2 ? 224 : 200);
+  static constexpr int kRegsSoftmax = QT == 2 ? 224 : 200;
   static constexpr uint32_t kTmemCols = DT == 1 ? 256 * QT : 512;
   static constexpr uint32_t kTmemAcc = 128 * QT;     // S buffers first (2 x 64 columns per tile), accumulators after
   static constexpr uint32_t kAccTile = 128 * DT;     // accumulator columns per Q tile: 2 streams x 64 DT
@@ -116,171 +110,15 @@ __device__ __forceinline__ int frame_of_block(int z, int N) {
   return z < N - 2 ? z + 1 : (z == N - 2 ? 0 : N - 1);
 }
 
-// ---- experimental split-row softmax (Shape::SP == 2): two threads per query row ----------------------------------
-// Warpgroup `half` (warps 4-7: 0, warps 8-11: 1) owns columns [32 half, 32 half + 32) of every 64-key score tile; warps w
-// and w + 4 share a TMEM lane quadrant, i.e. the same 32 query rows.  Per tile the two threads of a row exchange their
-// local maxima through shared memory (double-buffered by tile parity) under a 64-thread named barrier, so both use the
-// same reference maximum; each keeps a partial denominator, summed once in the epilogue.  Nobody writes P over the S
-// buffer before that barrier, i.e. before both halves have their scores in registers (P of half 1 lands on S columns of
-// half 0).  p_full counts 8 arrivals.  Everything else (barriers, phases, lazy rescale, epilogue formula) is the
-// one-thread-per-row protocol of the kernel below.
-template <typename T>
-__device__ __forceinline__ void softmax_split_rows(Barriers* bar, float* xch, uint32_t tmem, uint32_t tmem_acc, const TcArgs& a,
-                                                   const Segments& seg, const FramePlan& plan, int tiles, int n, int head,
-                                                   int row0, int warp, int lane) {
-  const int half = (warp - 4) >> 2;
-  const int quad = warp & 3;
-  const int r = quad * 32 + lane;   // query row within the tile
-  const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-  const uint32_t s_base = tmem + lane_base + TMEM_S;
-  const uint32_t acc_addr = tmem + lane_base + tmem_acc;
-  float* xmax = xch;        // [2 tile parities][2 halves][128 rows]
-  float* xl = xch + 512;    // [2 halves][2 streams][128 rows]
-  const float sl2 = a.scale_log2;
-  float m_st[2] = {-INFINITY, -INFINITY}, l_st[2] = {0.f, 0.f};
-  bool started[2] = {false, false};
-  int j = 0;
-  for (int g = 0; g < seg.count; ++g) {
-    const int feeds = seg.feeds[g];
-    const int primary = (feeds & 1) ? 0 : 1;
-    float m_ref = m_st[primary], l = l_st[primary];
-    const bool fresh = !started[primary];
-    for (int i = 0; i < tiles; ++i, ++j) {
-      const int b = j & 1;
-      const uint32_t s_addr = s_base + b * BN;
-      ptx::mbar_wait(&bar->s_full[0][b], (j >> 1) & 1);
-      ptx::tc_fence_after();
-      uint32_t sr[32];
-      ptx::tmem_ld32(s_addr + half * 32, sr);
-      ptx::tmem_wait_ld();
-      const int valid = a.L - i * BN - half * 32;  // keys of this half-tile that exist (may be <= 0)
-      if (valid < 32) {
-        asm volatile("" ::: "memory");
-#pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (e >= valid) sr[e] = __float_as_uint(-INFINITY);
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(sr[e]));
-        mx1 = fmaxf(mx1, __uint_as_float(sr[e + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(sr[e + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(sr[e + 3]));
-      }
-      const float mx_local = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      xmax[(b * 2 + half) * 128 + r] = mx_local;
-      ptx::named_bar_sync(1 + quad, 64);   // both halves hold their scores in registers; the maxima are visible
-      const float mx = fmaxf(mx_local, xmax[(b * 2 + (half ^ 1)) * 128 + r]);
-      if (i == 0 && fresh) {
-        m_ref = mx;
-      } else {
-        const bool grow = (mx - m_ref) * sl2 > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, grow)) {   // same decision in both warps of the row: identical inputs
-          ptx::mbar_wait(&bar->pv_done[0], (j - 1) & 1);
-          ptx::tc_fence_after();
-          const float m_new = grow ? mx : m_ref;
-          const float alpha = ptx::ex2((m_ref - m_new) * sl2);
-          l *= alpha;
-          m_ref = m_new;
-#pragma unroll
-          for (int st = 0; st < 2; ++st) {
-            if (!(feeds & (1 << st))) continue;
-            uint32_t o[32];   // this half rescales its 32 accumulator columns of the stream
-            ptx::tmem_ld32(acc_addr + st * D + half * 32, o);
-            ptx::tmem_wait_ld();
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              const float2 rr = ptx::mul2(make_float2(__uint_as_float(o[e]), __uint_as_float(o[e + 1])), make_float2(alpha, alpha));
-              o[e] = __float_as_uint(rr.x); o[e + 1] = __float_as_uint(rr.y);
-            }
-            ptx::tmem_st32(acc_addr + st * D + half * 32, o);
-          }
-        }
-      }
-      const float neg = -m_ref * sl2;
-      const float2 sl2v = make_float2(sl2, sl2), negv = make_float2(neg, neg);
-      float2 sumA = make_float2(0.f, 0.f), sumB = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        const float2 x = ptx::fma2(make_float2(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])), sl2v, negv);
-        sr[e] = __float_as_uint(x.x); sr[e + 1] = __float_as_uint(x.y);
-      }
-#pragma unroll
-      for (int e = 0; e < 32; ++e) sr[e] = __float_as_uint(ptx::ex2v(__uint_as_float(sr[e])));
-      uint32_t pk[16];
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) {
-        const float2 x0 = make_float2(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1]));
-        const float2 x1 = make_float2(__uint_as_float(sr[e + 2]), __uint_as_float(sr[e + 3]));
-        sumA = ptx::add2(sumA, x0);
-        sumB = ptx::add2(sumB, x1);
-        pk[e / 2] = pack2<T>(x0.x, x0.y);
-        pk[e / 2 + 1] = pack2<T>(x1.x, x1.y);
-      }
-      ptx::tmem_st16(s_addr + half * 16, pk);
-      l += (sumA.x + sumA.y) + (sumB.x + sumB.y);
-      ptx::tmem_wait_st();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar->p_full[0][b]);
-    }
-#pragma unroll
-    for (int st = 0; st < 2; ++st)
-      if (feeds & (1 << st)) { m_st[st] = m_ref; l_st[st] = l; started[st] = true; }
-  }
-  // ---- epilogue: this half stores columns [32 half, 32 half + 32) of the head ----
-  ptx::mbar_wait(&bar->acc_final[0], 0);
-  ptx::tc_fence_after();
-  xl[(half * 2 + 0) * 128 + r] = l_st[0];
-  xl[(half * 2 + 1) * 128 + r] = l_st[1];
-  ptx::named_bar_sync(1 + quad, 64);
-  const float lt[2] = {l_st[0] + xl[((half ^ 1) * 2 + 0) * 128 + r], l_st[1] + xl[((half ^ 1) * 2 + 1) * 128 + r]};
-  const float os = a.out_scale * (a.out_frame_scale ? a.out_frame_scale[n] : 1.f);
-  const float cf[2] = {seg.a_active ? os * plan.wA / lt[0] : 0.f, seg.b_active ? os * plan.wB / lt[1] : 0.f};
-  const bool active[2] = {seg.a_active, seg.b_active};
-  const int row = row0 + r;
-  if (half * 32 >= a.head_dim) return;   // padded columns (head_dim <= 32): nothing to store (the caller's final
-                                         // __syncthreads is reached after this function returns)
-  T* dst = (T*)a.out + ((long long)n * a.S + row) * (a.heads * a.head_dim) + head * a.head_dim + half * 32;
-  float acc[32];
-#pragma unroll
-  for (int e = 0; e < 32; ++e) acc[e] = 0.f;
-#pragma unroll
-  for (int st = 0; st < 2; ++st) {
-    if (!active[st]) continue;  // CTA-uniform
-    uint32_t o[32];
-    ptx::tmem_ld32(acc_addr + st * D + half * 32, o);
-    ptx::tmem_wait_ld();
-#pragma unroll
-    for (int e = 0; e < 32; ++e) acc[e] = fmaf(cf[st], __uint_as_float(o[e]), acc[e]);
-  }
-  if (row < a.S) {
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      if (half * 32 + v * 8 >= a.head_dim) break;
-      if (a.accumulate) {
-        const uint4 old = *reinterpret_cast<const uint4*>(dst + v * 8);
-        const T* o8 = reinterpret_cast<const T*>(&old);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[v * 8 + e] += to_f32(o8[e]);
-      }
-      *reinterpret_cast<uint4*>(dst + v * 8) =
-          make_uint4(pack2<T>(acc[v * 8], acc[v * 8 + 1]), pack2<T>(acc[v * 8 + 2], acc[v * 8 + 3]),
-                     pack2<T>(acc[v * 8 + 4], acc[v * 8 + 5]), pack2<T>(acc[v * 8 + 6], acc[v * 8 + 7]));
-    }
-  }
-}
-
-template <typename T, int QT, int DT, int SP>
-__global__ void __launch_bounds__(Shape<QT, DT, SP>::kThreads, Shape<QT, DT, SP>::kCtasPerSm)
+template <typename T, int QT, int DT>
+__global__ void __launch_bounds__(Shape<QT, DT>::kThreads, Shape<QT, DT>::kCtasPerSm)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ CUtensorMap tmK2,
                const __grid_constant__ CUtensorMap tmV2, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  using SH = Shape<QT, DT, SP>;
+  using SH = Shape<QT, DT>;
   constexpr int ST = SH::kStages;                  // (shadows the namespace constant: ring depth of this variant)
   constexpr uint32_t TMEM_ACC = SH::kTmemAcc;
   constexpr int QTILE = DT * Q_BYTES, KVTILE = DT * KV_BYTES;   // bytes of one Q / K / V tile (DT chunks)
@@ -303,7 +141,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int t = 0; t < QT; ++t) {
       for (int b = 0; b < 2; ++b) {
         ptx::mbar_init(&bar->s_full[t][b], 1);
-        ptx::mbar_init(&bar->p_full[t][b], 4 * SP);  // one arrive per softmax warp
+        ptx::mbar_init(&bar->p_full[t][b], 4);  // one arrive per softmax warp
       }
       ptx::mbar_init(&bar->pv_done[t], 1);
       ptx::mbar_init(&bar->acc_final[t], 1);
@@ -422,10 +260,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
   } else {
     ptx::setmaxnreg_inc<SH::kRegsSoftmax>();
-    if constexpr (SP == 2) {
-      softmax_split_rows<T>(bar, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bar) + 512), tmem, SH::kTmemAcc, a, seg,
-                            plan, tiles, n, head, row0, warp, lane);
-    } else {
     // ================================ softmax warpgroups ==========================
     const int t = (warp - 4) >> 2;   // Q tile of this warpgroup
     const int quad = warp & 3;       // TMEM lane quadrant of this warp
@@ -585,23 +419,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                            pack2<T>(acc[v * 8 + 4], acc[v * 8 + 5]), pack2<T>(acc[v * 8 + 6], acc[v * 8 + 7]));
       }
     }
-    }  // SP == 1
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) { __syncwarp(); ptx::tmem_dealloc(tmem, SH::kTmemCols); }
 }
 
-template <typename T, int QT, int DT, int SP = 1>
+template <typename T, int QT, int DT>
 int launch_t(const CUtensorMap* maps, const TcArgs& ta, cudaStream_t stream) {
-  auto kern = attn_tc_kernel<T, QT, DT, SP>;
-  constexpr int SMEM_BYTES = Shape<QT, DT, SP>::kSmemBytes, NUM_THREADS = Shape<QT, DT, SP>::kThreads;
+  auto kern = attn_tc_kernel<T, QT, DT>;
+  constexpr int SMEM_BYTES = Shape<QT, DT>::kSmemBytes, NUM_THREADS = Shape<QT, DT>::kThreads;
   static_assert(SMEM_BYTES <= 232448, "shared memory per CTA");
-  static bool configured = false;
-  if (!configured) {
-    PAID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
-  }
+  PAID_CUDA_CHECK(ensure_kernel_configured((const void*)kern, SMEM_BYTES, nullptr));
   dim3 grid((ta.S + QT * BM - 1) / (QT * BM), ta.heads, ta.N);
   profile_mark_begin(stream);
   PAID_CUDA_CHECK(launch_pdl(kern, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, maps[0], maps[1], maps[2], maps[3], maps[4],
@@ -614,9 +443,11 @@ int launch_t(const CUtensorMap* maps, const TcArgs& ta, cudaStream_t stream) {
 }  // namespace
 
 bool attn_tc_supported(const CoreArgs& a) {
-  const char* nopad = getenv("PAID_ATTN_NO_PAD");   // debugging: serve head_dim != 64 with the generic kernel
-  const char* cap = getenv("PAID_ATTN_MAX_TC_HEAD_DIM");   // debugging: larger head_dim goes to the generic kernel
-  const int max_hd = cap ? atoi(cap) : 3 * D;
+  // debugging knobs, read once: PAID_ATTN_NO_PAD=1 serves head_dim != 64 with the generic kernel,
+  // PAID_ATTN_MAX_TC_HEAD_DIM sends larger head_dim there
+  static const char* nopad = getenv("PAID_ATTN_NO_PAD");
+  static const char* cap = getenv("PAID_ATTN_MAX_TC_HEAD_DIM");
+  static const int max_hd = cap ? atoi(cap) : 3 * D;
   const bool padded_ok = a.head_dim != D && a.head_dim >= 16 && a.head_dim <= 3 * D && a.head_dim <= max_hd &&
                          a.head_dim % 8 == 0 && !(nopad && nopad[0] == '1');
   return (a.head_dim == D || padded_ok) && a.heads <= 65535 && a.N <= 65535 &&
@@ -656,15 +487,12 @@ int launch_attn_tc(const CoreArgs& a, cudaStream_t stream) {
   ta.scale_log2 = a.scale * kLog2e;
   ta.coef = a.coef; ta.out = a.out;
   ta.accumulate = a.accumulate; ta.out_scale = a.out_scale; ta.out_frame_scale = a.out_frame_scale;
-  const char* force = getenv("PAID_ATTN_QT");
+  const char* force = getenv("PAID_ATTN_QT");   // tests flip this between calls: not cached
   const bool single_tile = !(force && force[0] == '2');
   if (hd > 2 * D)
     return a.dtype == PAID_F16 ? launch_t<__half, 1, 3>(maps, ta, stream) : launch_t<__nv_bfloat16, 1, 3>(maps, ta, stream);
   if (hd > D)
     return a.dtype == PAID_F16 ? launch_t<__half, 1, 2>(maps, ta, stream) : launch_t<__nv_bfloat16, 1, 2>(maps, ta, stream);
-  const char* split = getenv("PAID_ATTN_SPLIT");   // experimental two-threads-per-row softmax (see Shape::SP)
-  if (single_tile && split && split[0] == '1')
-    return a.dtype == PAID_F16 ? launch_t<__half, 1, 1, 2>(maps, ta, stream) : launch_t<__nv_bfloat16, 1, 1, 2>(maps, ta, stream);
   if (single_tile)
     return a.dtype == PAID_F16 ? launch_t<__half, 1, 1>(maps, ta, stream) : launch_t<__nv_bfloat16, 1, 1>(maps, ta, stream);
   return a.dtype == PAID_F16 ? launch_t<__half, 2, 1>(maps, ta, stream) : launch_t<__nv_bfloat16, 2, 1>(maps, ta, stream);

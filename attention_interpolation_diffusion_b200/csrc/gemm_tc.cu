@@ -169,15 +169,8 @@ template <typename T, int BN>
 int launch_t(const CUtensorMap& tmA, const CUtensorMap* tmB, const GroupPtrs& gp, int groups, long long M, int N, int K,
              cudaStream_t stream) {
   auto kern = linear_tc_kernel<T, BN>;
-  static bool configured = false;
-  static int num_sms = 0;
-  if (!configured) {
-    PAID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
-    int dev = 0;
-    PAID_CUDA_CHECK(cudaGetDevice(&dev));
-    PAID_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
+  int num_sms = 0;
+  PAID_CUDA_CHECK(ensure_kernel_configured((const void*)kern, Cfg<BN>::kSmemBytes, &num_sms));
   const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = (N + BN - 1) / BN;
   const int total = m_tiles * n_tiles * groups;
   dim3 grid(total < num_sms ? total : num_sms);
@@ -328,15 +321,8 @@ template <typename T>
 int launch_pair_t(const CUtensorMap& tmA, const CUtensorMap* tmB, const GroupPtrs& gp, int groups, long long M, int N,
                   int K, cudaStream_t stream) {
   auto kern = linear_tc_pair_kernel<T>;
-  static bool configured = false;
-  static int num_sms = 0;
-  if (!configured) {
-    PAID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-    int dev = 0;
-    PAID_CUDA_CHECK(cudaGetDevice(&dev));
-    PAID_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
+  int num_sms = 0;
+  PAID_CUDA_CHECK(ensure_kernel_configured((const void*)kern, P_SMEM_BYTES, &num_sms));
   const int m_tiles = (int)((M + 255) / 256), n_tiles = (N + 255) / 256;
   const int total = m_tiles * n_tiles * groups;
   int pairs = num_sms / 2;
@@ -371,7 +357,8 @@ int launch_linear_tc_grouped(const void* x, const void* const* w, const void* co
   const bool wide = Nout % 256 == 0;
   // CTA pairs whenever the 256-wide tiles are at least 5/6 full (640 = 2.5 tiles still beats the 1-CTA kernel)
   const bool pairs_ok = M >= 256 && Nout >= 256 && 6 * Nout >= 5 * 256 * ((Nout + 255) / 256);
-  if (pairs_ok && !getenv("PAID_NO_CTA_PAIRS"))
+  static const bool no_pairs = getenv("PAID_NO_CTA_PAIRS") != nullptr;   // debugging knob, read once
+  if (pairs_ok && !no_pairs)
     return dtype == PAID_F16 ? launch_pair_t<__half>(tmA, tmB, gp, groups, M, Nout, K, stream)
                              : launch_pair_t<__nv_bfloat16>(tmA, tmB, gp, groups, M, Nout, K, stream);
   if (dtype == PAID_F16)

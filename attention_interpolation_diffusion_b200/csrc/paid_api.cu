@@ -28,6 +28,29 @@ std::atomic<uint64_t>& launch_counter() {
   return c;
 }
 
+cudaError_t ensure_kernel_configured(const void* kernel, int smem_bytes, int* num_sms) {
+  struct Entry { const void* kernel; int dev; };
+  static std::mutex mu;
+  static std::vector<Entry> done;
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  bool found = false;
+  for (const Entry& en : done) found = found || (en.kernel == kernel && en.dev == dev);
+  if (!found) {
+    if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)) != cudaSuccess) return e;
+    done.push_back({kernel, dev});
+  }
+  if (num_sms) {
+    if (dev < 0 || dev >= 64) return cudaDeviceGetAttribute(num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] == 0 && (e = cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    *num_sms = sms[dev];
+  }
+  return cudaSuccess;
+}
+
 static inline uint64_t align256(uint64_t b) { return (b + 255) & ~uint64_t(255); }
 
 struct Workspace {
@@ -63,7 +86,11 @@ static int validate(const PaidAttnParams* p, bool need_io) {
   if (!p->ctx && (p->L != p->S || p->Cc != p->C))
     return fail(PAID_EINVAL, "self-attention (ctx == NULL) needs L == S and Cc == C");
   if (!need_io) return PAID_OK;
-  if (!p->x || !p->wq || !p->wk || !p->wv || !p->wo || !p->y) return fail(PAID_EINVAL, "x, wq, wk, wv, wo, y must be non-NULL");
+  if (!p->x || !p->wq || !p->wo || !p->y) return fail(PAID_EINVAL, "x, wq, wo, y must be non-NULL");
+  if ((p->k_pre == nullptr) != (p->v_pre == nullptr)) return fail(PAID_EINVAL, "k_pre and v_pre must be given together");
+  if (!p->k_pre && (!p->wk || !p->wv)) return fail(PAID_EINVAL, "wk, wv must be non-NULL (or k_pre / v_pre given)");
+  if (p->kv_pre_broadcast && (!p->k_pre || p->mode != PAID_PLAIN))
+    return fail(PAID_EINVAL, "kv_pre_broadcast needs k_pre / v_pre and PLAIN mode");
   if (p->mode != PAID_PLAIN) {
     if (!p->coef) return fail(PAID_EINVAL, "coef is NULL");
     if (!p->kv_ext && (p->begin_frame < 0 || p->begin_frame >= p->N || p->end_frame < 0 || p->end_frame >= p->N))
@@ -139,7 +166,8 @@ static int core_dispatch(const CoreArgs& a, uint32_t flags, cudaStream_t stream)
   const bool padded = a.head_dim % 64 != 0;
   if (!(flags & PAID_FLAG_GENERIC_KERNELS) && attn_tc_supported(a) && !(padded && pad_rejected.load())) {
     *last_kernel_slot() = padded ? "tcgen05-padded" : "tcgen05";
-    st = launch_attn_tc(a, stream);
+    // single-stream modes at head_dim <= 64: the persistent dual-warpgroup kernel; OUTER and wide heads: attn_tc.cu
+    st = (!(flags & PAID_FLAG_ONE_WARPGROUP) && attn_dw_supported(a)) ? launch_attn_dw(a, stream) : launch_attn_tc(a, stream);
     if (st == PAID_EUNSUPPORTED && padded) {  // descriptor refused before any launch: other CUDA kernel family
       pad_rejected.store(true);
       *last_kernel_slot() = "generic";
@@ -349,6 +377,16 @@ int paid_attn_project_endpoints(const PaidAttnParams* p, int32_t local_frame, vo
   return linear_grouped(src, w, y, 2, p->L, p->C, p->Cc, p->dtype, p->flags, stream);
 }
 
+int paid_attn_project_kv(const PaidAttnParams* p, void* k_out, void* v_out, void* cuda_stream) {
+  int st = validate(p, false);
+  if (st != PAID_OK) return st;
+  if (!p->x || !p->wk || !p->wv || !k_out || !v_out) return fail(PAID_EINVAL, "x, wk, wv, k_out, v_out must be non-NULL");
+  const void* src = p->ctx ? p->ctx : p->x;
+  const void* w[2] = {p->wk, p->wv};
+  void* y[2] = {k_out, v_out};
+  return linear_grouped(src, w, y, 2, (long long)p->N * p->L, p->C, p->Cc, p->dtype, p->flags, (cudaStream_t)cuda_stream);
+}
+
 int paid_attn_forward(const PaidAttnParams* p, void* cuda_stream) {
   int st = validate(p, true);
   if (st != PAID_OK) return st;
@@ -364,7 +402,10 @@ int paid_attn_forward(const PaidAttnParams* p, void* cuda_stream) {
   const long long MS = (long long)p->N * p->S, ML = (long long)p->N * p->L;
 
   // interpolation.py:613, 623-624
-  if (!p->ctx) {  // self-attention: q, k, v share the input -> one launch
+  if (p->k_pre) {  // K / V of a step-invariant context were projected once per sequence (paid_attn_project_kv)
+    K = const_cast<void*>(p->k_pre); V = const_cast<void*>(p->v_pre);
+    if ((st = linear(p->x, p->wq, nullptr, Q, MS, p->C, p->C, p->dtype, p->flags, stream)) != PAID_OK) return st;
+  } else if (!p->ctx) {  // self-attention: q, k, v share the input -> one launch
     const void* w[3] = {p->wq, p->wk, p->wv};
     void* y[3] = {Q, K, V};
     if ((st = linear_grouped(p->x, w, y, 3, MS, p->C, p->C, p->dtype, p->flags, stream)) != PAID_OK) return st;
@@ -380,9 +421,14 @@ int paid_attn_forward(const PaidAttnParams* p, void* cuda_stream) {
   a.N = p->N; a.S = p->S; a.L = p->L; a.heads = p->heads; a.head_dim = p->C / p->heads;
   a.scale = p->scale; a.begin_frame = p->begin_frame; a.end_frame = p->end_frame;
   a.q = Q; a.k = K; a.v = V; a.coef = p->coef; a.out = H;
-  a.accumulate = 0; a.out_scale = 1.f; a.out_frame_scale = nullptr; a.stride0 = (long long)p->L * p->C;
+  a.accumulate = 0; a.out_scale = 1.f; a.out_frame_scale = nullptr;
+  a.stride0 = p->kv_pre_broadcast ? 0 : (long long)p->L * p->C;
   void* kx = p->mode == PAID_INNER ? base + ws.kx : nullptr;
   void* vx = p->mode == PAID_INNER ? base + ws.vx : nullptr;
+  // the endpoint K/V of a frame-sharded sequence arrive on another stream (NCCL broadcast): wait here, after the local
+  // projections have been queued
+  if (p->kv_ext_ready_event && p->mode != PAID_PLAIN)
+    PAID_CUDA_CHECK(cudaStreamWaitEvent(stream, (cudaEvent_t)p->kv_ext_ready_event, 0));
   if ((st = resolve_slots(a, p->mode == PAID_PLAIN ? nullptr : p->kv_ext, kx, vx, stream)) != PAID_OK) return st;
   // interpolation.py:627-664 / 760-790
   if ((st = core_dispatch(a, p->flags, stream)) != PAID_OK) return st;

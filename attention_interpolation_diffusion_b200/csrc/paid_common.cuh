@@ -135,6 +135,10 @@ struct CoreArgs {
   long long stride0;  // frame stride of k / v in elements (0: one matrix shared by all frames)
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-(kernel, device) attribute: set it the first time `kernel` is
+// launched on the current device (thread-safe).  Also returns the SM count of the current device.
+cudaError_t ensure_kernel_configured(const void* kernel, int smem_bytes, int* num_sms);
+
 // measurement hook (paid_attn_profile_*): called by the attention launchers immediately around the kernel launch
 void profile_mark_begin(cudaStream_t stream);
 void profile_mark_end(cudaStream_t stream);
@@ -150,6 +154,9 @@ bool linear_tc_supported(long long M, int Nout, int K);
 int launch_attn_generic(const CoreArgs& a, cudaStream_t stream);
 int launch_attn_tc(const CoreArgs& a, cudaStream_t stream);
 bool attn_tc_supported(const CoreArgs& a);
+// persistent dual-warpgroup kernel of the single-stream modes (PLAIN, INNER), head_dim <= 64 (attn_dw.cu)
+int launch_attn_dw(const CoreArgs& a, cudaStream_t stream);
+bool attn_dw_supported(const CoreArgs& a);
 int launch_geglu(const void* h, void* out, long long M, int D, int dtype, cudaStream_t stream);
 int launch_add_layer_norm(const void* x, const void* delta, const void* gamma, const void* beta, void* x_out, void* h_out,
                           long long rows, int C, float eps, int dtype, cudaStream_t stream);

@@ -29,7 +29,7 @@ import torch
 from torch import nn
 
 from . import _cabi
-from .attention import PaidAttnProcessor, check_unet_preconditions, split_ip_states
+from .attention import (PaidAttnProcessor, check_unet_preconditions, project_text_static, split_ip_states, static_kv)
 from .prior import generate_beta_tensor
 
 _coef_cache: dict = {}
@@ -67,6 +67,22 @@ class InterpolatedAttnProcessor(nn.Module):
         self.activated = True
         self.shard = None            # optional sharding.FrameShard
         self.kernel_flags = 0        # _cabi.FLAG_* (tests use FLAG_GENERIC_KERNELS as a cross-check)
+        self.coef_device = None      # optional fp32 device buffer holding the coefficients of the LOCAL frames; the step
+                                     # loop binds one buffer to every processor and rewrites it in place, so captured
+                                     # CUDA graphs serve any schedule (bind_coef_buffer)
+
+    def bind_coef_buffer(self, buf: Optional[torch.Tensor]):
+        self.coef_device = buf
+
+    def _coef_on(self, device, local_ids=None) -> torch.Tensor:
+        """fp32 device coefficients of the local frames: the bound buffer, else a cached upload of ``self.coef``."""
+        if self.coef_device is not None:
+            return self.coef_device
+        return _device_coef(self.coef if local_ids is None else self.coef[local_ids], device)
+
+    def project_static(self, attn, ctx, uniform, entry, endpoints=None):
+        """Per-sequence K / V of a step-invariant cross-attention context (attention.static_kv)."""
+        project_text_static(attn, ctx, uniform, entry, endpoints, self.kernel_flags)
 
     def deactivate(self):
         self.activated = False
@@ -99,14 +115,15 @@ class InterpolatedAttnProcessor(nn.Module):
         check_unet_preconditions(attn, hidden_states, attention_mask)
         x = hidden_states
         w = (attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, attn.to_out[0].weight, attn.to_out[0].bias)
+        st = static_kv(attn, encoder_hidden_states)
         if self.shard is not None:
-            return self.shard.run(self, attn, x, encoder_hidden_states, w)
+            return self.shard.run(self, attn, x, encoder_hidden_states, w, static=st)
         if x.shape[0] != self.size or self.coef.numel() != self.size:
             raise ValueError(f"batch size {x.shape[0]} / {self.coef.numel()} coefficients != processor size {self.size} "
                              "(the frames of one interpolation sequence must form the batch)")
-        coef = _device_coef(self.coef, x.device)
-        return _cabi.attn_forward(x, encoder_hidden_states, *w, coef, attn.heads, self.mode, self.is_fused, attn.scale,
-                                  flags=self.kernel_flags)
+        st = st or {}
+        return _cabi.attn_forward(x, encoder_hidden_states, *w, self._coef_on(x.device), attn.heads, self.mode, self.is_fused,
+                                  attn.scale, flags=self.kernel_flags, k_pre=st.get("k"), v_pre=st.get("v"))
 
     def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
                  attention_mask: Optional[torch.Tensor] = None, temb: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -164,7 +181,19 @@ class _InterpolatedIPAttnProcessor(InterpolatedAttnProcessor):
         self.scale = ip_attn.scale if hasattr(ip_attn, "scale") else None
         self.ip_attn = ip_attn
 
+    def project_static(self, attn, ctx, uniform, entry, endpoints=None):
+        """Text and image-token K / V of the sequence (both step-invariant), and for a frame-sharded sequence the endpoint
+        frames' K / V of both, projected locally from the endpoint contexts every rank holds."""
+        text, ip = split_ip_states(ctx, self.num_tokens, ctx.shape[0])
+        et = ei = None
+        if endpoints is not None:
+            et, ei = split_ip_states(endpoints, self.num_tokens, 2)
+        project_text_static(attn, text, uniform, entry, et, self.kernel_flags)
+        project_text_static(attn, ip, uniform, entry, ei, self.kernel_flags, prefix="ip_",
+                            wk=self.ip_attn.to_k_ip[0].weight, wv=self.ip_attn.to_v_ip[0].weight)
+
     def _parts(self, attn, hidden_states, encoder_hidden_states, attention_mask):
+        """(x, st, coef, q, k, v, kip, vip): projections of the call; K / V from the per-sequence cache when attached."""
         check_unet_preconditions(attn, hidden_states, attention_mask)
         x = hidden_states
         sh = self.shard
@@ -177,37 +206,46 @@ class _InterpolatedIPAttnProcessor(InterpolatedAttnProcessor):
             raise ValueError(f"batch size {frames} != processor size {self.size}")
         if self.coef.numel() != self.size:
             raise ValueError(f"{self.coef.numel()} coefficients != processor size {self.size}")
+        coef = self._coef_on(x.device, None if sh is None else sh.frame_ids)
+        q = _cabi.linear(x, attn.to_q.weight, flags=self.kernel_flags)
+        st = static_kv(attn, encoder_hidden_states)
+        if st is not None:
+            return x, st, coef, q, st["k"], st["v"], st.get("ip_k"), st.get("ip_v")
         text, ip = (None, None) if encoder_hidden_states is None else split_ip_states(
             encoder_hidden_states, self.num_tokens, frames)
-        coef = _device_coef(self.coef if sh is None else self.coef[sh.lo:sh.hi], x.device)
         src = x if text is None else text
-        q = _cabi.linear(x, attn.to_q.weight, flags=self.kernel_flags)
         k = _cabi.linear(src, attn.to_k.weight, flags=self.kernel_flags)
         v = _cabi.linear(src, attn.to_v.weight, flags=self.kernel_flags)
-        return x, ip, coef, q, k, v
+        kip = vip = None
+        if ip is not None:
+            kip, vip = self._ip_kv(ip)
+        return x, {}, coef, q, k, v, kip, vip
 
-    def _endpoints(self, k, v, need_begin: bool = True):
-        """Frame-sharded call: keyword arguments for ``attn_core`` that carry the endpoint K/V of the whole sequence
-        (rows of the local k / v on the ranks that own frame 0 / N-1, broadcast to the others -- the one collective of
-        the path, sharding.py).  Unsharded: the endpoints are rows 0 and -1 of the batch (no arguments)."""
+    def _endpoints(self, attn, k, v, st: dict, key: str = "kv_ext", cross: bool = False):
+        """Frame-sharded call: keyword arguments for ``attn_core`` that carry the endpoint K/V of the whole sequence.
+        Rank 0 holds both endpoint frames (its local frames 0 and 1).  Cross-attention endpoints come from the
+        per-sequence cache (projected locally on every rank, no collective); self-attention endpoints are rows of rank
+        0's K / V, broadcast to the others -- the one collective of the path (sharding.py).  Unsharded: the endpoints
+        are rows 0 and -1 of the batch (no arguments)."""
         sh = self.shard
         if sh is None:
             return {}
-        from .sharding import broadcast_endpoints
-        kv = torch.empty(4, k.shape[1], k.shape[2], dtype=k.dtype, device=k.device)
-        own_b, own_e = sh.rank == sh.begin_owner, sh.rank == sh.end_owner
-        if own_b and need_begin:
-            kv[0].copy_(k[0]), kv[1].copy_(v[0])
-        if own_e:
-            kv[2].copy_(k[-1]), kv[3].copy_(v[-1])
-        if not need_begin:
-            kv[0:2].zero_()            # never read by the kernel's consumers; keep the buffer defined
-        if sh.world_size > 1:
-            if need_begin:
-                broadcast_endpoints(kv, sh.begin_owner, sh.end_owner, sh.group)
-            else:
-                torch.distributed.broadcast(kv[2:4], src=sh.end_owner, group=sh.group)
-        return dict(kv_ext=kv, begin_frame=0 if own_b else -1, end_frame=k.shape[0] - 1 if own_e else -1)
+        if sh.owns_endpoints and (cross or sh.world_size == 1):
+            return dict(begin_frame=0, end_frame=1)
+        if cross:
+            if key not in st:
+                raise RuntimeError("a frame-sharded IP-Adapter cross-attention call needs the per-sequence K/V cache with "
+                                   "the endpoint contexts (InterpolationPipeline attaches it)")
+            return dict(kv_ext=st[key], begin_frame=-1, end_frame=-1)
+        kv = sh.kv_buffer(id(attn), k.shape[1], k.shape[2], k)
+        if sh.owns_endpoints:
+            kv[0].copy_(k[0]), kv[1].copy_(v[0]), kv[2].copy_(k[1]), kv[3].copy_(v[1])
+        ev = sh.exchange(kv, ready_on_main=sh.owns_endpoints)
+        if sh.owns_endpoints:
+            return dict(begin_frame=0, end_frame=1)
+        if ev is not None:
+            torch.cuda.current_stream(k.device).wait_event(ev)
+        return dict(kv_ext=kv, begin_frame=-1, end_frame=-1)
 
     def _ip_kv(self, ip):
         return (_cabi.linear(ip, self.ip_attn.to_k_ip[0].weight, flags=self.kernel_flags),
@@ -225,13 +263,14 @@ class OuterInterpolatedIPAttnProcessor(_InterpolatedIPAttnProcessor):
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
         if not self.activated:
             return self.ip_attn(attn, hidden_states, encoder_hidden_states, attention_mask, temb)
-        x, ip, coef, q, k, v = self._parts(attn, hidden_states, encoder_hidden_states, attention_mask)
+        cross = encoder_hidden_states is not None
+        x, st, coef, q, k, v, kip, vip = self._parts(attn, hidden_states, encoder_hidden_states, attention_mask)
         hid = _cabi.attn_core(q, k, v, coef, attn.heads, _cabi.PAID_OUTER, self.is_fused, attn.scale, flags=self.kernel_flags,
-                              **self._endpoints(k, v))
-        if ip is not None:
-            kip, vip = self._ip_kv(ip)
+                              **self._endpoints(attn, k, v, st, "kv_ext", cross))
+        if kip is not None:
             _cabi.attn_core(q, kip, vip, coef, attn.heads, _cabi.PAID_OUTER, self.is_fused, attn.scale, flags=self.kernel_flags,
-                            out=hid, accumulate=True, out_scale=float(self.scale[0]), **self._endpoints(kip, vip))
+                            out=hid, accumulate=True, out_scale=float(self.scale[0]),
+                            **self._endpoints(attn, kip, vip, st, "ip_kv_ext", True))
         return self._out(attn, hid)
 
 
@@ -244,11 +283,11 @@ class InnerInterpolatedIPAttnProcessor(_InterpolatedIPAttnProcessor):
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
         if not self.activated:
             return self.ip_attn(attn, hidden_states, encoder_hidden_states, attention_mask, temb)
-        x, ip, coef, q, k, v = self._parts(attn, hidden_states, encoder_hidden_states, attention_mask)
+        cross = encoder_hidden_states is not None
+        x, st, coef, q, k, v, kip, vip = self._parts(attn, hidden_states, encoder_hidden_states, attention_mask)
         hid = _cabi.attn_core(q, k, v, coef, attn.heads, _cabi.PAID_INNER, self.is_fused, attn.scale, flags=self.kernel_flags,
-                              **self._endpoints(k, v))
-        if ip is not None:
-            kip, vip = self._ip_kv(ip)
+                              **self._endpoints(attn, k, v, st, "kv_ext", cross))
+        if kip is not None:
             _cabi.attn_core(q, kip, vip, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale, flags=self.kernel_flags,
                             out=hid, accumulate=True, out_scale=float(self.scale[0]))
         return self._out(attn, hid)
@@ -259,18 +298,32 @@ class ScaleControlIPAttnProcessor(_InterpolatedIPAttnProcessor):
     ``coef[n]`` times the attention over the END frame's image tokens (reference interpolation.py:51-211)."""
     mode = _cabi.PAID_OUTER
 
+    def project_static(self, attn, ctx, uniform, entry, endpoints=None):
+        super().project_static(attn, ctx, uniform, entry, endpoints)
+        # the end image for every frame (reference: ip[0][6:9]): the last frame of the batch, or, frame-sharded, the
+        # end-frame context every rank holds
+        text, ip = split_ip_states(ctx if endpoints is None else endpoints, self.num_tokens, (ctx if endpoints is None else endpoints).shape[0])
+        project_text_static(attn, ip[-1:], True, entry, None, self.kernel_flags, prefix="ip_end_",
+                            wk=self.ip_attn.to_k_ip[0].weight, wv=self.ip_attn.to_v_ip[0].weight)
+
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
-        x, ip, coef, q, k, v = self._parts(attn, hidden_states, encoder_hidden_states, attention_mask)
+        cross = encoder_hidden_states is not None
+        x, st, coef, q, k, v, kip, vip = self._parts(attn, hidden_states, encoder_hidden_states, attention_mask)
         if self.activated:
             hid = _cabi.attn_core(q, k, v, coef, attn.heads, _cabi.PAID_OUTER, self.is_fused, attn.scale, flags=self.kernel_flags,
-                                  **self._endpoints(k, v))
+                                  **self._endpoints(attn, k, v, st, "kv_ext", cross))
         else:
-            hid = _cabi.attn_core(q, k, v, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale, flags=self.kernel_flags)
-        if ip is not None:
-            kip, vip = self._ip_kv(ip[-1:].contiguous())          # the end image for every frame (ip[0][6:9])
-            if self.shard is not None:                            # ... which lives on the rank that owns frame N-1
-                kv = self._endpoints(kip, vip, need_begin=False)["kv_ext"]
-                kip, vip = kv[2:3], kv[3:4]
-            _cabi.attn_core(q, kip, vip, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale, flags=self.kernel_flags,
+            hid = _cabi.attn_core(q, k, v, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale, flags=self.kernel_flags,
+                                  kv_broadcast=st.get("broadcast", False))
+        if kip is not None:
+            if "ip_end_k" in st:
+                kend, vend = st["ip_end_k"], st["ip_end_v"]
+            elif self.shard is not None and self.shard.world_size > 1:
+                raise RuntimeError("a frame-sharded scale-control call needs the per-sequence K/V cache (the end frame's "
+                                   "image tokens live on rank 0)")
+            else:                      # the end image for every frame (ip[0][6:9]): the last frame of the batch
+                end = 1 if self.shard is not None else kip.shape[0] - 1
+                kend, vend = kip[end:end + 1].contiguous(), vip[end:end + 1].contiguous()
+            _cabi.attn_core(q, kend, vend, None, attn.heads, _cabi.PAID_PLAIN, False, attn.scale, flags=self.kernel_flags,
                             out=hid, accumulate=True, out_frame_scale=coef, kv_broadcast=True)
         return self._out(attn, hid)

@@ -71,27 +71,39 @@ def slerp(v0: torch.Tensor, v1: torch.Tensor, t: float, threshold: float = 0.999
 
 class _GraphedForward:
     """One UNet forward (fixed processor state and shapes) captured into a CUDA graph.  The ~2400 kernel launches
-    of a forward otherwise cost ~100 ms of host time, more than the GPU needs to execute them."""
+    of a forward otherwise cost ~100 ms of host time, more than the GPU needs to execute them.  A frame-sharded
+    forward captures its NCCL broadcasts and the side stream they run on as well (every rank captures and replays
+    the same sequence of collectives)."""
 
-    def __init__(self, unet, sample, t, ctx, added):
+    def __init__(self, unet, sample, t, ctx, added, shard=None):
         from . import _cabi
         dev = sample.device
         self.sample, self.ctx = sample.clone(), ctx.clone()
         self.t = torch.zeros(1, device=dev, dtype=torch.float32)
         self.added = None if added is None else {k: v.clone() for k, v in added.items()}
         self.t.fill_(float(t))
+        self.shard = shard
+
+        def run():
+            if shard is not None:
+                shard.begin_forward(dev)
+            out = unet(self.sample, self.t, self.ctx, self.added)
+            if shard is not None:
+                shard.end_forward(dev)
+            return out
+
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):      # warm-up outside capture: cuDNN autotune, lazy init, coef upload, workspace
+        with torch.cuda.stream(side):      # warm-up outside capture: cuDNN autotune, lazy init, NCCL channels, workspace
             for _ in range(2):
-                unet(self.sample, self.t, self.ctx, self.added)
+                run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.workspace = _cabi._workspaces.get(dev)      # keep the scratch buffer the graph points into alive
         n0 = _cabi.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = unet(self.sample, self.t, self.ctx, self.added)
+            self.out = run()
         self.launches = _cabi.launch_count() - n0       # libpaid_attn kernels inside one replay
 
     def __call__(self, sample, t, ctx, added):
@@ -106,16 +118,33 @@ class _GraphedForward:
 
 
 class InterpolationPipeline:
-    def __init__(self, unet: UNetHarness, shard: Optional[FrameShard] = None, use_cuda_graphs: bool = True):
+    MAX_GRAPHS = 6       # captured forwards kept alive (each owns a private memory pool): 3 per (shape, processor set)
+
+    def __init__(self, unet: UNetHarness, shard: Optional[FrameShard] = None, use_cuda_graphs: bool = True,
+                 cache_static_kv: bool = True):
         self.unet = unet
         self.scheduler = DDIMScheduler()
         self.shard = shard
         self.use_cuda_graphs = use_cuda_graphs
-        self._graphs: dict = {}
+        self.cache_static_kv = cache_static_kv
+        self._graphs: dict = {}            # insertion-ordered: oldest first (LRU eviction)
+        self._coef_buf: Optional[torch.Tensor] = None     # fp32 coefficients of the local frames, shared by all processors
+        self._kv_tag = [None]              # the pass whose cached cross-attention K/V the processors read ("cond" / "uncond")
         self.graph_kernel_launches = 0     # libpaid_attn kernels executed through graph replays
         self.load_aid()
 
     # ---- processor install / toggle (sdxl:1066-1136) ---------------------------------------------
+    def _installed(self):
+        for name, proc in self.unet.attn_processors.items():
+            if not name.startswith("encoder"):
+                yield name, proc
+
+    def _after_install(self):
+        self._graphs.clear()               # captured forwards bake the processor objects in
+        self._coef_buf = None
+        for _, m in self.unet._attention_modules().items():
+            m.paid_kv, m.paid_kv_tag = None, self._kv_tag
+
     def load_aid(self, t: Optional[float] = 0.5, is_fused: bool = True, atype: str = "fused_outer", size: int = 7,
                  alpha: float = 1, beta: float = 1):
         cls = {"fused_outer": OuterInterpolatedAttnProcessor, "fused_inner": InnerInterpolatedAttnProcessor}[atype]
@@ -125,13 +154,15 @@ class InterpolationPipeline:
                 original = getattr(old, "original_attn", None) or old
                 if isinstance(original, (OuterInterpolatedAttnProcessor, InnerInterpolatedAttnProcessor)):
                     original = None
+                if hasattr(original, "ip_attn") or isinstance(original, PaidIPAdapterAttnProcessor):
+                    original = None        # an IP-Adapter processor set was installed before: back to stock attention
                 proc = cls(t=t, size=size, is_fused=is_fused, alpha=alpha, beta=beta, original_attn=original)
                 proc.shard = self.shard
                 attn_procs[name] = proc
             else:
                 attn_procs[name] = old
         self.unet.set_attn_processor(attn_procs)
-        self._graphs.clear()               # captured forwards bake the processor objects in
+        self._after_install()
 
     def load_aid_ip_adapter(self, num_tokens: int = 16, scale: float = 1.0, t: Optional[float] = 0.5,
                             is_fused: bool = True, early: str = "fused_outer", size: int = 7, alpha: float = 1,
@@ -153,61 +184,107 @@ class InterpolationPipeline:
             attn_procs[name] = cls(t=t, size=size, is_fused=is_fused, alpha=alpha, beta=beta, ip_attn=old)
             attn_procs[name].shard = self.shard
         self.unet.set_attn_processor(attn_procs)
-        self._graphs.clear()
+        self._after_install()
 
     def activate_aid(self, it: float):
-        for name, proc in self.unet.attn_processors.items():
-            if not name.startswith("encoder"):
-                proc.activate(it)
+        for _, proc in self._installed():
+            proc.activate(it)
 
     def deactivate_aid(self):
-        for name, proc in self.unet.attn_processors.items():
-            if not name.startswith("encoder"):
-                proc.deactivate()
+        for _, proc in self._installed():
+            proc.deactivate()
 
     def set_coefs(self, coef: torch.Tensor):
-        """N-frame extension of activate_aid: one coefficient per frame."""
-        for name, proc in self.unet.attn_processors.items():
-            if not name.startswith("encoder"):
-                proc.set_coefs(coef)
+        """N-frame extension of activate_aid: one coefficient per frame.  On CUDA the values also go into ONE fp32 device
+        buffer that every processor reads (its address is what captured graphs hold; a new schedule rewrites it in place)."""
+        for _, proc in self._installed():
+            proc.set_coefs(coef)
+
+    def _bind_coefs(self, coef: torch.Tensor, device: torch.device):
+        """Install the schedule on every processor and refresh the shared device buffer (local frames only)."""
+        self.set_coefs(coef)
+        if device.type != "cuda":
+            return
+        local = coef.detach().float().clone()
+        local[0], local[-1] = 0, 1
+        if self.shard is not None:
+            local = local[self.shard.frame_ids]
+        if self._coef_buf is None or self._coef_buf.numel() != local.numel() or self._coef_buf.device != device:
+            self._coef_buf = torch.empty(local.numel(), dtype=torch.float32, device=device)
+            self._graphs.clear()
+        self._coef_buf.copy_(local)
+        for _, proc in self._installed():
+            proc.bind_coef_buffer(self._coef_buf)
+
+    def _refresh_static_kv(self, cond, uncond, uncond_uniform: bool, cond_endpoints):
+        """K / V of the prompt embeddings of every cross-attention layer, once per sequence (SURVEY.md section 8f rank 1;
+        the reference re-projects them in all 100 UNet calls, interpolation.py:623-624).  The unconditional pass carries
+        the same negative prompt in every frame: one (L, C) K/V pair serves all frames (kv_broadcast)."""
+        if not (self.cache_static_kv and cond.is_cuda):
+            for _, m in self.unet._attention_modules().items():
+                m.paid_kv = None
+            return
+        for name, m in self.unet._attention_modules().items():
+            if not name.endswith("attn2.processor"):
+                continue
+            proc = m.processor
+            if m.paid_kv is None:
+                m.paid_kv = {"cond": {}, "uncond": {}}
+            for tag, ctx, uniform, ends in (("cond", cond, False, cond_endpoints), ("uncond", uncond, uncond_uniform, None)):
+                entry = m.paid_kv[tag]
+                entry.pop("reallocated", None)
+                proc.project_static(m, ctx, uniform, entry, ends)
+                if entry.pop("reallocated", False):
+                    self._graphs.clear()       # captured forwards point into the old buffers
 
     # ---- the step loop ---------------------------------------------------------------------------
     @torch.no_grad()
     def _denoise(self, latents, cond, uncond, added_cond, added_uncond, coef, num_inference_steps, guidance_scale,
-                 warmup_ratio):
+                 warmup_ratio, uncond_uniform: bool = False, cond_endpoints=None):
         """latents (n,4,H,W); cond / uncond (n,77,Cc): the local frames.  Returns final latents."""
         self.scheduler.set_timesteps(num_inference_steps)
         warmup_steps = int(num_inference_steps * warmup_ratio)
         latents = latents * self.scheduler.init_noise_sigma
-        # multi-rank shards launch eagerly: the per-layer NCCL broadcast inside a captured forward is untested on this
-        # stack (PAID_SHARD_GRAPHS=1 opts in, every rank captures the same sequence of collectives)
-        graphs = (self.use_cuda_graphs and latents.is_cuda and
-                  (self.shard is None or self.shard.world_size == 1 or os.environ.get("PAID_SHARD_GRAPHS") == "1"))
+        multi_rank = self.shard is not None and self.shard.world_size > 1
+        # PAID_SHARD_GRAPHS=0: launch a multi-rank forward eagerly (A/B timing of the captured NCCL broadcasts)
+        graphs = self.use_cuda_graphs and latents.is_cuda and not (multi_rank and os.environ.get("PAID_SHARD_GRAPHS") == "0")
+        self._bind_coefs(coef, latents.device)
+        if self.shard is not None:
+            self.shard.static_endpoints = cond_endpoints
+        self._refresh_static_kv(cond, uncond, uncond_uniform, cond_endpoints if self.shard is not None else None)
         for i, t in enumerate(self.scheduler.timesteps.tolist()):
             model_in = self.scheduler.scale_model_input(latents, t)
-            noise_text = self._forward(i < warmup_steps, coef, model_in, t, cond, added_cond, graphs)
+            noise_text = self._forward(i < warmup_steps, "cond", model_in, t, cond, added_cond, graphs)
             if graphs:
                 noise_text = noise_text.clone()      # the next replay may reuse the same static output
-            noise_uncond = self._forward(False, coef, model_in, t, uncond, added_uncond, graphs)
+            noise_uncond = self._forward(False, "uncond", model_in, t, uncond, added_uncond, graphs)
             noise = noise_uncond + guidance_scale * (noise_text - noise_uncond)
             latents = self.scheduler.step(noise, t, latents)
         return latents
 
-    def _set_mode(self, aid: bool, coef):
-        if aid:
-            self.set_coefs(coef)      # AID on (conditional pass of the first warmup_steps steps, sdxl:2245-2246)
-        else:
-            self.deactivate_aid()     # stock attention (sdxl:2248, 2272)
+    def _set_mode(self, aid: bool):
+        for _, proc in self._installed():
+            proc.activated = bool(aid)      # AID on: conditional pass of the first warmup_steps steps (sdxl:2245-2248, 2272)
 
-    def _forward(self, aid: bool, coef, sample, t, ctx, added, graphs: bool):
+    def _forward(self, aid: bool, tag: str, sample, t, ctx, added, graphs: bool):
+        self._kv_tag[0] = tag
         if not graphs:
-            self._set_mode(aid, coef)
-            return self.unet(sample, t, ctx, added)
-        key = (aid, tuple(float(c) for c in coef) if aid else None, tuple(sample.shape), tuple(ctx.shape), sample.dtype)
-        g = self._graphs.get(key)
+            self._set_mode(aid)
+            if self.shard is not None:
+                self.shard.begin_forward(sample.device)
+            out = self.unet(sample, t, ctx, added)
+            if self.shard is not None:
+                self.shard.end_forward(sample.device)
+            return out
+        # the coefficient VALUES are not part of the key: they live in the shared device buffer (_bind_coefs)
+        key = (aid, tag, tuple(sample.shape), tuple(ctx.shape), sample.dtype)
+        g = self._graphs.pop(key, None)
         if g is None:
-            self._set_mode(aid, coef)
-            g = self._graphs[key] = _GraphedForward(self.unet, sample, t, ctx, added)
+            self._set_mode(aid)
+            while len(self._graphs) >= self.MAX_GRAPHS:
+                self._graphs.pop(next(iter(self._graphs)))     # least recently used
+            g = _GraphedForward(self.unet, sample, t, ctx, added, self.shard)
+        self._graphs[key] = g                                  # most recently used last
         self.graph_kernel_launches += g.launches
         return g(sample, t, ctx, added)
 
@@ -225,7 +302,8 @@ class InterpolationPipeline:
                     guidance_scale: Optional[float] = None, warmup_ratio: float = 0.5, coef: Optional[torch.Tensor] = None,
                     ip_start=None, ip_end=None, ip_negative=None):
         """N-frame AID / PAID in one batch.  latent_* (1,4,H,W); embeds_* (1,77,Cc); pooled_* (1,1280) for SDXL.
-        Interior frames take lerped embeddings, or ``guide_embeds`` when given (PAID).  Returns this rank's frames.
+        Interior frames take lerped embeddings, or ``guide_embeds`` when given (PAID).  Returns this rank's frames
+        (frame-sharded: in the shard's local order, ``FrameShard.frame_ids``).
 
         Image-conditioned morphing (after ``load_aid_ip_adapter``; reference sdxl:2144-2197): ``ip_start`` / ``ip_end``
         (1,T,Cc) are the projected IP-Adapter image tokens of the two endpoint images; frame i gets their lerp by c_i
@@ -256,6 +334,7 @@ class InterpolationPipeline:
         if self.unet.cfg.text_time:
             pooled_c = frames(pooled_start, pooled_end, pooled_guide)
             pooled_u = pooled_negative.expand(size, -1).contiguous()
+        cond_endpoints = torch.stack([cond[0], cond[-1]]).contiguous()     # the endpoint prompts (every rank holds them)
         if self.shard is not None:
             sl = self.shard.local
             lat, cond, uncond = sl(lat).contiguous(), sl(cond).contiguous(), sl(uncond).contiguous()
@@ -263,7 +342,8 @@ class InterpolationPipeline:
                 pooled_c, pooled_u = sl(pooled_c).contiguous(), sl(pooled_u).contiguous()
         n = lat.shape[0]
         return self._denoise(lat, cond, uncond, self._added(n, pooled_c, lat.device, lat.dtype),
-                             self._added(n, pooled_u, lat.device, lat.dtype), coef, num_inference_steps, g, warmup_ratio)
+                             self._added(n, pooled_u, lat.device, lat.dtype), coef, num_inference_steps, g, warmup_ratio,
+                             uncond_uniform=True, cond_endpoints=cond_endpoints)
 
     @torch.no_grad()
     def interpolate_candidates(self, ts, latent_start, latent_end, embeds_start, embeds_end, negative_embeds, **kw):

@@ -13,6 +13,7 @@
  *   paid_attn_core               attn.get_attention_scores + torch.bmm + alpha-lerp
  *                                                                         interpolation.py:627-664, 760-790
  *   paid_linear                  attn.to_q / to_k / to_v / to_out[0]      interpolation.py:613, 623-624, 666
+ *   paid_attn_project_kv         attn.to_k / to_v of a step-invariant context, once per sequence  interpolation.py:623-624
  *   paid_attn_project_endpoints  key[0:1], key[-1:], value[0:1], value[-1:] interpolation.py:627-630
  *                                (for frame-sharded execution: the owner rank
  *                                projects, NCCL broadcasts, every rank consumes
@@ -38,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PAID_ABI_VERSION 1
+#define PAID_ABI_VERSION 2
 
 typedef enum PaidStatus {
   PAID_OK = 0,
@@ -59,6 +60,8 @@ typedef enum PaidMode {
 
 /* flags */
 #define PAID_FLAG_GENERIC_KERNELS 1u /* force the generic-shape CUDA kernels (validation cross-check) */
+#define PAID_FLAG_ONE_WARPGROUP 2u   /* PLAIN / INNER: use the one-softmax-warpgroup tcgen05 kernel (attn_tc.cu) instead of
+                                      * the persistent dual-warpgroup one (attn_dw.cu); cross-check and A/B timing */
 
 typedef struct PaidAttnParams {
   uint32_t struct_size; /* sizeof(PaidAttnParams), ABI guard */
@@ -91,6 +94,20 @@ typedef struct PaidAttnParams {
   void* y;          /* (N,S,C) output */
   void* workspace;  /* >= paid_attn_workspace_bytes(p) bytes, 256-byte aligned */
   uint64_t workspace_bytes;
+  /* ---- ABI 2 ----
+   * K and V of the context produced earlier (paid_attn_project_kv): the text prompt of a cross-attention layer does not
+   * change over the denoising loop (pipeline_interpolated_sdxl.py:2232-2345 passes the same prompt_embeds every step),
+   * so the caller projects it once per sequence.  (N,L,C) each, or one (L,C) matrix shared by every frame when
+   * kv_pre_broadcast is 1 (PLAIN mode only: the unconditional pass, whose N frames carry the same negative prompt).
+   * NULL: project ctx (or x) with wk / wv inside this call. */
+  const void* k_pre;
+  const void* v_pre;
+  int32_t kv_pre_broadcast;
+  int32_t reserved0;
+  /* cudaEvent_t (or NULL): the stream waits for it after the local projections and before the attention core -- the
+   * endpoint K/V in kv_ext are being delivered on another stream (the NCCL broadcast of a frame-sharded sequence),
+   * so the transfer overlaps the q/k/v projection of the local frames. */
+  void* kv_ext_ready_event;
 } PaidAttnParams;
 
 /* attention on already projected tensors (head h of frame n lives at [n, t, h*d : (h+1)*d]) */
@@ -132,6 +149,10 @@ int paid_attn_core(const PaidCoreParams* p, void* cuda_stream);
 /* K and V of one local frame: k_out, v_out are (L,C).  Uses p->x / p->ctx, p->wk, p->wv. */
 int paid_attn_project_endpoints(const PaidAttnParams* p, int32_t local_frame, void* k_out, void* v_out,
                                 void* cuda_stream);
+
+/* K and V of all N frames of the context (interpolation.py:623-624): k_out, v_out are (N,L,C), to be handed back through
+ * PaidAttnParams.k_pre / v_pre on later calls.  Uses p->x / p->ctx, p->wk, p->wv, p->N, p->L, p->C, p->Cc. */
+int paid_attn_project_kv(const PaidAttnParams* p, void* k_out, void* v_out, void* cuda_stream);
 
 /* y (M,Nout) = x (M,K) * w(Nout,K)^T + bias(Nout or NULL) */
 int paid_linear(const void* x, const void* w, const void* bias, void* y, int64_t M, int32_t Nout, int32_t K,

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(cabi):
     assert set(names) == set(cabi.EXPORTS)
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.paid_attn_abi_version() == 1
+    assert lib.paid_attn_abi_version() == 2
 
 
 def test_struct_layout_matches_header(cabi):

@@ -8,21 +8,28 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import paid_oracle as O
-from attention_interpolation_diffusion_b200.sharding import (FrameShard, broadcast_endpoints, endpoint_owners,
-                                                             plan_frame_shards)
+from attention_interpolation_diffusion_b200.sharding import FrameShard, plan_frame_shards
 
 
 def test_plan():
-    assert plan_frame_shards(7, 2) == [(0, 4), (4, 7)]
-    assert plan_frame_shards(16, 8) == [(2 * i, 2 * i + 2) for i in range(8)]
-    assert plan_frame_shards(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
-    assert endpoint_owners(plan_frame_shards(3, 4), 3) == (0, 2)
-    assert endpoint_owners(plan_frame_shards(7, 1), 7) == (0, 0)
+    assert plan_frame_shards(7, 2) == [[0, 6, 1, 2], [3, 4, 5]]
+    assert plan_frame_shards(16, 8) == [[0, 15]] + [[2 * i - 1, 2 * i] for i in range(1, 8)]
+    assert plan_frame_shards(7, 1) == [[0, 6, 1, 2, 3, 4, 5]]
+    for bad in ((3, 4), (8, 8), (2, 2), (1, 1)):
+        with pytest.raises(ValueError):        # rank 0 holds both endpoints, every other rank at least one frame
+            plan_frame_shards(*bad)
     for n in range(2, 40):
         for w in (1, 2, 4, 8):
+            if w > 1 and w > n - 1:
+                continue
             sh = plan_frame_shards(n, w)
-            assert sh[0][0] == 0 and sh[-1][1] == n and all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
-            assert max(h - l for l, h in sh) - min(h - l for l, h in sh) <= 1
+            assert sorted(f for part in sh for f in part) == list(range(n))
+            assert sh[0][:2] == [0, n - 1]                                   # both endpoints on rank 0, local frames 0 and 1
+            assert max(map(len, sh)) - min(map(len, sh)) <= 1 and min(map(len, sh)) >= 1
+    s0 = FrameShard(0, 2, 7)
+    x = torch.arange(7.0).reshape(7, 1)
+    parts = [FrameShard(r, 2, 7).local(x) for r in range(2)]
+    assert parts[0].flatten().tolist() == [0, 6, 1, 2] and torch.equal(s0.unshard(parts), x)
 
 
 def _worker(rank, world, port, q):
@@ -36,12 +43,12 @@ def _worker(rank, world, port, q):
         full = O.forward_direct(x, None, w, coef, O.MODE_OUTER, True)
         sh = FrameShard(rank, world, N)
         xl = sh.local(x)
-        kv = torch.zeros(4, S, C, dtype=torch.float64)
-        if rank == sh.begin_owner:
-            kv[0], kv[1] = xl[0] @ w.wk.T, xl[0] @ w.wv.T
-        if rank == sh.end_owner:
-            kv[2], kv[3] = xl[-1] @ w.wk.T, xl[-1] @ w.wv.T
-        broadcast_endpoints(kv, sh.begin_owner, sh.end_owner)
+        # the product's exchange: rank 0 fills the layer's buffer from its two endpoint frames, ONE broadcast
+        kv = sh.kv_buffer("layer0", S, C, xl)
+        if sh.owns_endpoints:
+            kv[0], kv[1], kv[2], kv[3] = xl[0] @ w.wk.T, xl[0] @ w.wv.T, xl[1] @ w.wk.T, xl[1] @ w.wv.T
+        assert sh.exchange(kv, ready_on_main=sh.owns_endpoints) is None          # CPU tensors: ordered, no event
+        assert sh.broadcasts == 1 and sh.kv_buffer("layer0", S, C, xl) is kv      # persistent per layer
         y = O.forward_direct(xl, None, w, sh.local(coef), O.MODE_OUTER, True, kv_endpoints=tuple(kv))
         q.put((rank, float((y - sh.local(full)).abs().max())))
     finally:
@@ -62,13 +69,13 @@ def test_two_rank_endpoint_broadcast():
 
 
 def _ip_worker(rank, world, port, q):
-    """Frame-sharded IP-Adapter call: the PRODUCT's endpoint exchange (_InterpolatedIPAttnProcessor._endpoints: rows of
-    the local K/V on the owner ranks, broadcast over the process group) feeds the oracle's per-rank math."""
+    """Frame-sharded IP-Adapter call: the PRODUCT's endpoint routing (_InterpolatedIPAttnProcessor._endpoints: rank 0's
+    rows broadcast for self-attention, locally projected endpoint contexts for cross-attention) feeds the oracle's
+    per-rank math."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from attention_interpolation_diffusion_b200 import (OuterInterpolatedIPAttnProcessor, PaidIPAdapterAttnProcessor,
-                                                            ScaleControlIPAttnProcessor)
+        from attention_interpolation_diffusion_b200 import OuterInterpolatedIPAttnProcessor, PaidIPAdapterAttnProcessor
         N, S, C, h, Cc, L, T = 6, 20, 64, 2, 48, 9, 4
         dt = torch.float64
         w = O.make_layer(C, Cc, h, 5, dt)
@@ -81,23 +88,32 @@ def _ip_worker(rank, world, port, q):
         ql, kl, vl, kipl, vipl = O._ip_parts(sh.local(x), sh.local(ctx), sh.local(ip), w, wk_ip, wv_ip)
         cl = sh.local(coef)
         errs = []
-        # outer-IP: text and image-token endpoints both exchanged
+        # outer-IP self-attention form: the endpoints are rows of rank 0's K / V, broadcast (the one collective)
         proc = OuterInterpolatedIPAttnProcessor(size=N, is_fused=True, alpha=3, beta=3, ip_attn=ipa)
         proc.shard = sh
-        et, ei = proc._endpoints(kl, vl), proc._endpoints(kipl, vipl)
-        assert et["begin_frame"] == (0 if rank == sh.begin_owner else -1)
-        assert et["end_frame"] == (sh.local_frames - 1 if rank == sh.end_owner else -1)
-        hid = O._direct_core(ql, kl, vl, tuple(et["kv_ext"]), cl, O.MODE_OUTER, True, scale, h)
-        hid = hid + 0.6 * O._direct_core(ql, kipl, vipl, tuple(ei["kv_ext"]), cl, O.MODE_OUTER, True, scale, h)
+        layer = object()
+        et = proc._endpoints(layer, kl, vl, {}, "kv_ext", cross=False)
+        assert (et["begin_frame"], et["end_frame"]) == ((0, 1) if sh.owns_endpoints else (-1, -1))
+        ends_t = (kl[0], vl[0], kl[1], vl[1]) if sh.owns_endpoints else tuple(et["kv_ext"])
+        # cross-attention form (text and image tokens): every rank projects the endpoint contexts itself, no collective
+        ce, ie = torch.stack([ctx[0], ctx[-1]]), torch.stack([ip[0], ip[-1]])
+        st = {"kv_ext": torch.stack([ce[0] @ w.wk.T, ce[0] @ w.wv.T, ce[1] @ w.wk.T, ce[1] @ w.wv.T]),
+              "ip_kv_ext": torch.stack([ie[0] @ wk_ip.T, ie[0] @ wv_ip.T, ie[1] @ wk_ip.T, ie[1] @ wv_ip.T])}
+        before = sh.broadcasts
+        ec, ei = proc._endpoints(layer, kl, vl, st, "kv_ext", cross=True), proc._endpoints(layer, kipl, vipl, st, "ip_kv_ext", cross=True)
+        assert sh.broadcasts == before
+        ends_c = (kl[0], vl[0], kl[1], vl[1]) if sh.owns_endpoints else tuple(ec["kv_ext"])
+        ends_i = (kipl[0], vipl[0], kipl[1], vipl[1]) if sh.owns_endpoints else tuple(ei["kv_ext"])
+        assert max(float((a - b).abs().max()) for a, b in zip(ends_t, ends_c)) < 1e-12       # both routes agree
+        hid = O._direct_core(ql, kl, vl, ends_c, cl, O.MODE_OUTER, True, scale, h)
+        hid = hid + 0.6 * O._direct_core(ql, kipl, vipl, ends_i, cl, O.MODE_OUTER, True, scale, h)
         full = O.forward_ip_outer(x, ctx, ip, w, wk_ip, wv_ip, coef, True, 0.6)
         errs.append(float((hid @ w.wo.T + w.bo - sh.local(full)).abs().max()))
-        # scale control: only the END frame's image-token K/V travel
-        proc = ScaleControlIPAttnProcessor(size=N, is_fused=True, alpha=3, beta=3, ip_attn=ipa)
-        proc.shard = sh
-        kv = proc._endpoints(kipl[-1:], vipl[-1:], need_begin=False)["kv_ext"]
+        # scale control: the END frame's image-token K/V for every frame, from the end-frame context every rank holds
         n = sh.local_frames
-        hid = O._direct_core(ql, kl, vl, tuple(et["kv_ext"]), cl, O.MODE_OUTER, True, scale, h)
-        hid = hid + cl.reshape(n, 1, 1) * O._direct_core(ql, kv[2:3].expand(n, -1, -1), kv[3:4].expand(n, -1, -1), None, None,
+        kend, vend = (ip[-1:] @ wk_ip.T), (ip[-1:] @ wv_ip.T)
+        hid = O._direct_core(ql, kl, vl, ends_c, cl, O.MODE_OUTER, True, scale, h)
+        hid = hid + cl.reshape(n, 1, 1) * O._direct_core(ql, kend.expand(n, -1, -1), vend.expand(n, -1, -1), None, None,
                                                          O.MODE_PLAIN, False, scale, h)
         full = O.forward_ip_scale_control(x, ctx, ip, w, wk_ip, wv_ip, coef, True, True)
         errs.append(float((hid @ w.wo.T + w.bo - sh.local(full)).abs().max()))
