@@ -23,7 +23,7 @@ from typing import Optional
 
 import torch
 
-from .attention import PaidIPAdapterAttnProcessor
+from .attention import PaidAttnProcessor, PaidIPAdapterAttnProcessor
 from .interpolation import (InnerInterpolatedAttnProcessor, InnerInterpolatedIPAttnProcessor,
                             OuterInterpolatedAttnProcessor, OuterInterpolatedIPAttnProcessor,
                             ScaleControlIPAttnProcessor)
@@ -139,6 +139,19 @@ class InterpolationPipeline:
             if not name.startswith("encoder"):
                 yield name, proc
 
+    @staticmethod
+    def _stock(proc):
+        """The stock attention processor underneath whatever AID wrapper is installed (the reference captures
+        ``AttnProcessor2_0`` as ``original_attn``, sdxl:1076)."""
+        for _ in range(4):
+            inner = getattr(proc, "original_attn", None) or getattr(proc, "ip_attn", None)
+            if inner is None:
+                break
+            proc = inner
+        wrappers = (OuterInterpolatedAttnProcessor, InnerInterpolatedAttnProcessor, OuterInterpolatedIPAttnProcessor,
+                    InnerInterpolatedIPAttnProcessor, ScaleControlIPAttnProcessor, PaidIPAdapterAttnProcessor)
+        return PaidAttnProcessor() if proc is None or isinstance(proc, wrappers) else proc
+
     def _after_install(self):
         self._graphs.clear()               # captured forwards bake the processor objects in
         self._coef_buf = None
@@ -151,12 +164,7 @@ class InterpolationPipeline:
         attn_procs = {}
         for name, old in self.unet.attn_processors.items():
             if not name.startswith("encoder"):
-                original = getattr(old, "original_attn", None) or old
-                if isinstance(original, (OuterInterpolatedAttnProcessor, InnerInterpolatedAttnProcessor)):
-                    original = None
-                if hasattr(original, "ip_attn") or isinstance(original, PaidIPAdapterAttnProcessor):
-                    original = None        # an IP-Adapter processor set was installed before: back to stock attention
-                proc = cls(t=t, size=size, is_fused=is_fused, alpha=alpha, beta=beta, original_attn=original)
+                proc = cls(t=t, size=size, is_fused=is_fused, alpha=alpha, beta=beta, original_attn=self._stock(old))
                 proc.shard = self.shard
                 attn_procs[name] = proc
             else:
@@ -179,8 +187,8 @@ class InterpolationPipeline:
             if name.endswith("attn2.processor"):
                 old = PaidIPAdapterAttnProcessor(m.to_q.in_features, m.to_k.in_features, (num_tokens,), scale)
                 old = old.to(device=m.to_q.weight.device, dtype=m.to_q.weight.dtype)
-            elif isinstance(old, (OuterInterpolatedAttnProcessor, InnerInterpolatedAttnProcessor)):
-                old = old.original_attn
+            else:
+                old = self._stock(old)
             attn_procs[name] = cls(t=t, size=size, is_fused=is_fused, alpha=alpha, beta=beta, ip_attn=old)
             attn_procs[name].shard = self.shard
         self.unet.set_attn_processor(attn_procs)

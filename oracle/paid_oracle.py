@@ -201,6 +201,25 @@ def forward_chunked(x, ctx, w: LayerWeights, coef, mode: int, fused: bool,
     return hid @ w.wo.T + w.bo
 
 
+def forward_rows(x, ctx, w: LayerWeights, coef, mode: int, fused: bool, rows, scale: Optional[float] = None) -> torch.Tensor:
+    """forward_direct restricted to the query rows ``rows`` (index tensor / list) of every frame: (N, len(rows), C).
+    Exact (query rows do not interact); K / V are projected for all tokens, so a full-size layer (S = 4096, N = 16 / 32)
+    is checked in seconds on a row sample."""
+    N = x.shape[0]
+    h = w.heads
+    scale = (x.shape[-1] // h) ** -0.5 if scale is None else scale
+    rows = torch.as_tensor(rows, dtype=torch.long)
+    src = x if ctx is None else ctx
+    q = x[:, rows] @ w.wq.T                                 # interpolation.py:613
+    k, v = src @ w.wk.T, src @ w.wv.T                       # interpolation.py:623-624
+    ends = (k[0], v[0], k[-1], v[-1])
+    hid = torch.empty_like(q)
+    for n in range(N):
+        hid[n:n + 1] = _direct_core(q[n:n + 1], k[n:n + 1], v[n:n + 1], ends, None if coef is None else coef[n:n + 1],
+                                    mode, fused, scale, h)
+    return hid @ w.wo.T + w.bo
+
+
 # ----------------------------------------------------------------------------
 # formulation 2: partial attentions + log-sum-exp merge (what the kernels do)
 # ----------------------------------------------------------------------------
