@@ -27,7 +27,7 @@ EXPORTS = [
     "paid_attn_abi_version", "paid_attn_workspace_bytes", "paid_attn_core_workspace_bytes", "paid_attn_forward",
     "paid_attn_core", "paid_attn_project_endpoints", "paid_attn_project_kv", "paid_linear", "paid_attn_last_error",
     "paid_attn_launch_count", "paid_attn_last_kernel", "paid_attn_profile_enable", "paid_attn_profile_read",
-    "paid_geglu", "paid_add_layer_norm", "paid_group_norm_nhwc", "paid_group_norm_workspace_bytes",
+    "paid_linear_geglu", "paid_geglu", "paid_add_layer_norm", "paid_group_norm_nhwc", "paid_group_norm_workspace_bytes",
     "paid_residual_bias_add",
 ]
 
@@ -89,6 +89,9 @@ def load_library() -> C.CDLL:
     lib.paid_linear.restype = C.c_int
     lib.paid_linear.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                 C.c_int32, C.c_uint32, C.c_void_p]
+    lib.paid_linear_geglu.restype = C.c_int
+    lib.paid_linear_geglu.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_uint32, C.c_void_p]
     lib.paid_geglu.restype = C.c_int
     lib.paid_geglu.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.paid_add_layer_norm.restype = C.c_int
@@ -256,6 +259,20 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     y = torch.empty(*x.shape[:-1], w.shape[0], dtype=x.dtype, device=x.device) if out is None else out
     _check(lib.paid_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), M, w.shape[0], K, _dtype_code(x),
                            flags, _stream(x)), "paid_linear")
+    return y
+
+
+def linear_geglu(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
+    """``paid_linear_geglu``: (x Wa^T + ba) * gelu(x Wg^T + bg) for w = [Wa ; Wg] (2D, K): the feed-forward's first
+    Linear with GEGLU in the GEMM epilogue; returns (..., D)."""
+    lib = load_library()
+    _dev_check(x, w, bias)
+    K = x.shape[-1]
+    M = x.numel() // K
+    D = w.shape[0] // 2
+    y = torch.empty(*x.shape[:-1], D, dtype=x.dtype, device=x.device)
+    _check(lib.paid_linear_geglu(x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), M, D, K, _dtype_code(x), flags,
+                                 _stream(x)), "paid_linear_geglu")
     return y
 
 

@@ -172,6 +172,35 @@ class Attention(nn.Module):
     def set_processor(self, processor):
         self.processor = processor
 
+    # ---- the helper methods of diffusers' Attention that the REFERENCE processors call (interpolation.py:604, 614,
+    # 637-659).  The processors of this package never use them (their kernels read heads in place
+    # and never materialise the probabilities); they make this class a faithful host for the unmodified reference
+    # processors, which is how oracle/gen_e2e_golden.py produces the end-to-end reference latents.
+    def prepare_attention_mask(self, attention_mask, target_length, batch_size, out_dim=3):
+        if attention_mask is not None:
+            raise NotImplementedError("attention_mask must be None")
+        return None
+
+    def head_to_batch_dim(self, tensor, out_dim=3):
+        b, t, c = tensor.shape
+        return tensor.reshape(b, t, self.heads, c // self.heads).permute(0, 2, 1, 3).reshape(b * self.heads, t, c // self.heads)
+
+    def batch_to_head_dim(self, tensor):
+        bh, t, d = tensor.shape
+        return tensor.reshape(bh // self.heads, self.heads, t, d).permute(0, 2, 1, 3).reshape(bh // self.heads, t, d * self.heads)
+
+    def get_attention_scores(self, query, key, attention_mask=None):
+        if attention_mask is not None:
+            raise NotImplementedError("attention_mask must be None")
+        dtype = query.dtype
+        if self.upcast_attention:
+            query, key = query.float(), key.float()
+        scores = torch.baddbmm(torch.empty(query.shape[0], query.shape[1], key.shape[1], dtype=query.dtype, device=query.device),
+                               query, key.transpose(-1, -2), beta=0, alpha=self.scale)
+        if self.upcast_softmax:
+            scores = scores.float()
+        return scores.softmax(dim=-1).to(dtype)
+
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kw):
         return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
                               attention_mask=attention_mask, **kw)

@@ -29,6 +29,29 @@ struct GroupPtrs {
   void* y[3];
 };
 
+// 32 output columns of a GEGLU tile: out = (a + ba) * gelu(g + bg); bias is (2 N,) = [ba ; bg] or NULL
+template <typename T>
+__device__ __forceinline__ void geglu_store(T* __restrict__ dst, const uint32_t (&ra)[32], const uint32_t (&rg)[32],
+                                            const T* __restrict__ bias, int col0, int N) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {  // 8 columns = 16 bytes per store
+    const int col = col0 + v * 8;
+    if (col >= N) break;
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a0 = __uint_as_float(ra[v * 8 + 2 * j]), a1 = __uint_as_float(ra[v * 8 + 2 * j + 1]);
+      float g0 = __uint_as_float(rg[v * 8 + 2 * j]), g1 = __uint_as_float(rg[v * 8 + 2 * j + 1]);
+      if (bias) {
+        a0 += to_f32(bias[col + 2 * j]); a1 += to_f32(bias[col + 2 * j + 1]);
+        g0 += to_f32(bias[N + col + 2 * j]); g1 += to_f32(bias[N + col + 2 * j + 1]);
+      }
+      o[j] = pack2<T>(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
+    }
+    *reinterpret_cast<uint4*>(dst + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 template <int BN> struct Cfg {
   static constexpr int kStages = BN == 256 ? 4 : 6;
   static constexpr int kBBytes = BN * BK * 2;
@@ -37,11 +60,16 @@ template <int BN> struct Cfg {
   static constexpr int kTmemCols = 2 * BN;  // two accumulators
 };
 
-template <typename T, int BN>
+// GEGLU = true (BN = 256 only): w is (2 N, K) = [Wa ; Wg]; an output tile is 128 columns wide, its weight tile is rows
+// [n0, n0 + 128) of Wa and of Wg, so accumulator columns 0..127 hold a and 128..255 hold g of the SAME output columns and
+// the epilogue writes (a + ba) * gelu(g + bg): the feed-forward's first Linear and its GEGLU in one kernel.
+template <typename T, int BN, bool GEGLU>
 __global__ void __launch_bounds__(192, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
                  const GroupPtrs gp, long long M, int N, int K, int m_tiles, int n_tiles, int total_tiles) {
+  static_assert(!GEGLU || BN == 256, "the GEGLU epilogue pairs two 128-column halves");
+  constexpr int TILE_N = GEGLU ? 128 : BN;   // output columns per tile
   using C = Cfg<BN>;
   constexpr int ST = C::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -72,7 +100,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   // tile -> (group, m block, n block); n fastest
   auto decode = [&](int tile, int& group, long long& m0, int& n0) {
-    n0 = (tile % n_tiles) * BN;
+    n0 = (tile % n_tiles) * TILE_N;
     const int r = tile / n_tiles;
     m0 = (long long)(r % m_tiles) * BM;
     group = r / m_tiles;
@@ -92,7 +120,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* a = smem + s * C::kStageBytes;
           ptx::tma_load_2d(a, &tmA, &full[s], kb * BK, (int)m0);
           ptx::tma_load_2d(a + A_BYTES, tmB, &full[s], kb * BK, n0);
-          if (BN == 256) ptx::tma_load_2d(a + A_BYTES + 128 * BK * 2, tmB, &full[s], kb * BK, n0 + 128);
+          if (BN == 256) ptx::tma_load_2d(a + A_BYTES + 128 * BK * 2, tmB, &full[s], kb * BK, GEGLU ? N + n0 : n0 + 128);
         }
       }
     }
@@ -131,6 +159,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_wait(&acc_full[ab], (tc >> 1) & 1);
       ptx::tc_fence_after();
       const long long row = m0 + quad * 32 + lane;
+      if constexpr (GEGLU) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t ra[32], rg[32];
+          ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * BN + c * 32, ra);
+          ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * BN + 128 + c * 32, rg);
+          ptx::tmem_wait_ld();
+          const int col0 = n0 + c * 32;
+          if (row < M && col0 < N) geglu_store<T>(y + row * N + col0, ra, rg, bias, col0, N);
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -154,6 +193,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      }
       // this accumulator buffer may be overwritten by the tile after next
       ptx::tc_fence_before();
       __syncwarp();
@@ -165,13 +205,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) { __syncwarp(); ptx::tmem_dealloc(tmem, C::kTmemCols); }
 }
 
-template <typename T, int BN>
+template <typename T, int BN, bool GEGLU = false>
 int launch_t(const CUtensorMap& tmA, const CUtensorMap* tmB, const GroupPtrs& gp, int groups, long long M, int N, int K,
              cudaStream_t stream) {
-  auto kern = linear_tc_kernel<T, BN>;
+  auto kern = linear_tc_kernel<T, BN, GEGLU>;
   int num_sms = 0;
   PAID_CUDA_CHECK(ensure_kernel_configured((const void*)kern, Cfg<BN>::kSmemBytes, &num_sms));
-  const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = (N + BN - 1) / BN;
+  constexpr int TILE_N = GEGLU ? 128 : BN;
+  const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = (N + TILE_N - 1) / TILE_N;
   const int total = m_tiles * n_tiles * groups;
   dim3 grid(total < num_sms ? total : num_sms);
   PAID_CUDA_CHECK(launch_pdl(kern, grid, dim3(192), Cfg<BN>::kSmemBytes, stream, tmA, tmB[0], tmB[1], tmB[2], gp, M, N, K,
@@ -190,7 +231,7 @@ constexpr int P_STAGES = 6;
 constexpr int P_STAGE_BYTES = A_BYTES + 128 * BK * 2;  // per CTA: 128 rows of x + 128 rows of w
 constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256;
 
-template <typename T>
+template <typename T, bool GEGLU>
 __global__ void __launch_bounds__(192, 1)
 linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                       const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
@@ -224,8 +265,11 @@ linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
 
+  // GEGLU: an output tile is 256 rows x 128 columns; CTA 0 holds rows [n0, n0 + 128) of Wa, CTA 1 the same rows of Wg
+  // (w is (2 N, K) = [Wa ; Wg]), so accumulator columns 0..127 are a and 128..255 are g of the same output columns
+  constexpr int TILE_N = GEGLU ? 128 : 256;
   auto decode = [&](int tile, int& group, long long& m0, int& n0) {
-    n0 = (tile % n_tiles) * 256;
+    n0 = (tile % n_tiles) * TILE_N;
     const int r = tile / n_tiles;
     m0 = (long long)(r % m_tiles) * 256;
     group = r / m_tiles;
@@ -245,7 +289,7 @@ linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&full[s]), 0));
           uint8_t* a = smem + s * P_STAGE_BYTES;
           ptx::tma_load_2d_pair(a, &tmA, &full[s], kb * BK, (int)m0 + (int)rank * 128);
-          ptx::tma_load_2d_pair(a + A_BYTES, tmB, &full[s], kb * BK, n0 + (int)rank * 128);
+          ptx::tma_load_2d_pair(a + A_BYTES, tmB, &full[s], kb * BK, GEGLU ? n0 + (int)rank * N : n0 + (int)rank * 128);
         }
       }
     }
@@ -284,6 +328,17 @@ linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       ptx::mbar_wait(&acc_full[ab], (tc >> 1) & 1);
       ptx::tc_fence_after();
       const long long row = m0 + rank * 128 + quad * 32 + lane;
+      if constexpr (GEGLU) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t ra[32], rg[32];
+          ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * 256 + c * 32, ra);
+          ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * 256 + 128 + c * 32, rg);
+          ptx::tmem_wait_ld();
+          const int col0 = n0 + c * 32;
+          if (row < M && col0 < N) geglu_store<T>(y + row * N + col0, ra, rg, bias, col0, N);
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         uint32_t r[32];
@@ -307,6 +362,7 @@ linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
         }
       }
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&acc_empty[ab]), 0));
@@ -317,13 +373,13 @@ linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 1) { __syncwarp(); ptx::tmem_dealloc_pair(tmem, 512); }
 }
 
-template <typename T>
+template <typename T, bool GEGLU = false>
 int launch_pair_t(const CUtensorMap& tmA, const CUtensorMap* tmB, const GroupPtrs& gp, int groups, long long M, int N,
                   int K, cudaStream_t stream) {
-  auto kern = linear_tc_pair_kernel<T>;
+  auto kern = linear_tc_pair_kernel<T, GEGLU>;
   int num_sms = 0;
   PAID_CUDA_CHECK(ensure_kernel_configured((const void*)kern, P_SMEM_BYTES, &num_sms));
-  const int m_tiles = (int)((M + 255) / 256), n_tiles = (N + 255) / 256;
+  const int m_tiles = (int)((M + 255) / 256), n_tiles = GEGLU ? (N + 127) / 128 : (N + 255) / 256;
   const int total = m_tiles * n_tiles * groups;
   int pairs = num_sms / 2;
   if (total < pairs) pairs = total;
@@ -366,6 +422,29 @@ int launch_linear_tc_grouped(const void* x, const void* const* w, const void* co
                 : launch_t<__half, 128>(tmA, tmB, gp, groups, M, Nout, K, stream);
   return wide ? launch_t<__nv_bfloat16, 256>(tmA, tmB, gp, groups, M, Nout, K, stream)
               : launch_t<__nv_bfloat16, 128>(tmA, tmB, gp, groups, M, Nout, K, stream);
+}
+
+bool linear_geglu_tc_supported(long long M, int D, int K) {
+  return M >= 1 && D % 8 == 0 && K % 8 == 0 && (M + BM - 1) / BM < (1 << 22);
+}
+
+// y (M, D) = (x Wa^T + ba) * gelu(x Wg^T + bg), w = [Wa ; Wg] (2 D, K), bias = [ba ; bg] (2 D,) or NULL
+int launch_linear_geglu_tc(const void* x, const void* w, const void* bias, void* y, long long M, int D, int K, int dtype,
+                           cudaStream_t stream) {
+  if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y | (uintptr_t)bias) & 15) return fail(PAID_EINVAL, "linear_geglu: pointers must be 16-byte aligned");
+  CUtensorMap tmA, tmB[3];
+  GroupPtrs gp{};
+  int st = make_tmap_2d(&tmA, x, dtype, M, K, K, BM);
+  if (st != PAID_OK) return st;
+  if ((st = make_tmap_2d(&tmB[0], w, dtype, 2LL * D, K, K, 128)) != PAID_OK) return st;
+  tmB[1] = tmB[2] = tmB[0];
+  gp.bias[0] = bias; gp.y[0] = y;
+  static const bool no_pairs = getenv("PAID_NO_CTA_PAIRS") != nullptr;
+  if (M >= 256 && D >= 128 && !no_pairs)
+    return dtype == PAID_F16 ? launch_pair_t<__half, true>(tmA, tmB, gp, 1, M, D, K, stream)
+                             : launch_pair_t<__nv_bfloat16, true>(tmA, tmB, gp, 1, M, D, K, stream);
+  return dtype == PAID_F16 ? launch_t<__half, 256, true>(tmA, tmB, gp, 1, M, D, K, stream)
+                           : launch_t<__nv_bfloat16, 256, true>(tmA, tmB, gp, 1, M, D, K, stream);
 }
 
 int launch_linear_tc(const void* x, const void* w, const void* bias, void* y, long long M, int Nout, int K, int dtype,

@@ -67,6 +67,76 @@ int launch_linear_generic(const void* x, const void* w, const void* bias, void* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// y (M,D) = (x Wa^T + ba) * gelu(x Wg^T + bg), w = [Wa ; Wg] (2D,K): any-shape counterpart of the GEGLU epilogue of
+// gemm_tc.cu (cross-check, and K / D that TMA cannot address)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) linear_geglu_generic_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                                   const T* __restrict__ bias, T* __restrict__ y,
+                                                                   long long M, int D, int K) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ba[16][64 + 4];
+  __shared__ float Bg[16][64 + 4];
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.y * 64;
+  const int n0 = blockIdx.x * 64;
+  const int tr = tid / 16, tc = tid % 16;
+  float acc_a[4][4] = {}, acc_g[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = tid; i < 1024; i += 256) {
+      int r = i / 16, kk = i % 16;
+      long long gm = m0 + r;
+      int gn = n0 + r, gk = k0 + kk;
+      As[kk][r] = (gm < M && gk < K) ? to_f32(x[gm * K + gk]) : 0.f;
+      Ba[kk][r] = (gn < D && gk < K) ? to_f32(w[(long long)gn * K + gk]) : 0.f;
+      Bg[kk][r] = (gn < D && gk < K) ? to_f32(w[(long long)(D + gn) * K + gk]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], ba[4], bg[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][tr * 4 + i]; ba[i] = Ba[kk][tc * 4 + i]; bg[i] = Bg[kk][tc * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc_a[i][j] = fmaf(a[i], ba[j], acc_a[i][j]);
+          acc_g[i][j] = fmaf(a[i], bg[j], acc_g[i][j]);
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long gm = m0 + tr * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + tc * 4 + j;
+      if (gn < D) {
+        const float av = acc_a[i][j] + (bias ? to_f32(bias[gn]) : 0.f);
+        const float gv = acc_g[i][j] + (bias ? to_f32(bias[D + gn]) : 0.f);
+        y[gm * D + gn] = from_f32<T>(av * gelu_erf(gv));
+      }
+    }
+  }
+}
+
+int launch_linear_geglu_generic(const void* x, const void* w, const void* bias, void* y, long long M, int D, int K, int dtype,
+                                cudaStream_t stream) {
+  dim3 grid((D + 63) / 64, (unsigned)((M + 63) / 64));
+  if (dtype == PAID_F16)
+    linear_geglu_generic_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)x, (const __half*)w, (const __half*)bias,
+                                                                  (__half*)y, M, D, K);
+  else
+    linear_geglu_generic_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, M, D, K);
+  PAID_LAUNCH_CHECK("linear_geglu_generic_kernel");
+  return PAID_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // endpoint lerp for INNER mode: kx[n] = (1-c_n) kb + c_n ke, vx likewise  (interpolation.py:772-775)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -108,21 +178,6 @@ int launch_lerp_endpoints(const void* kb, const void* vb, const void* ke, const 
 // GEGLU: out[m, j] = h[m, j] * gelu(h[m, D + j]), exact erf GELU.  HBM-bound: 16-byte loads / stores,
 // 6 bytes of traffic per output element.
 // ------------------------------------------------------------------------------------------------
-// exact-form GELU 0.5 g (1 + erf(g / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the
-// 16-bit output rounding): one MUFU.RCP, one MUFU.EX2 and 7 FMA-pipe instructions instead of erff's ~30.
-__device__ __forceinline__ float gelu_erf(float g) {
-  const float z = fabsf(g) * 0.70710678118654752f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float erfc_z = p * t * exp2f(-z * z * 1.4426950408889634f);   // 1 - erf(|g| / sqrt 2)
-  const float half_g = 0.5f * g;
-  // g >= 0: 0.5 g (2 - erfc) ;  g < 0: 0.5 g erfc
-  return g >= 0.f ? fmaf(-half_g, erfc_z, g) : half_g * erfc_z;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256) geglu_kernel(const T* __restrict__ h, T* __restrict__ out, unsigned total, unsigned vec_per_row) {
   // 32-bit index arithmetic (the launcher checks M * D / 8 < 2^31): a 64-bit division per vector costs more than the math

@@ -270,6 +270,16 @@ int paid_linear(const void* x, const void* w, const void* bias, void* y, int64_t
   return linear(x, w, bias, y, M, Nout, K, dtype, flags, (cudaStream_t)cuda_stream);
 }
 
+int paid_linear_geglu(const void* x, const void* w, const void* bias, void* y, int64_t M, int32_t D, int32_t K,
+                      int32_t dtype, uint32_t flags, void* cuda_stream) {
+  if (!x || !w || !y) return fail(PAID_EINVAL, "paid_linear_geglu: x, w, y must be non-NULL");
+  if (M <= 0 || D <= 0 || K <= 0) return fail(PAID_EINVAL, "paid_linear_geglu: sizes must be positive");
+  if (dtype != PAID_F16 && dtype != PAID_BF16) return fail(PAID_EINVAL, "paid_linear_geglu: bad dtype");
+  if (!(flags & PAID_FLAG_GENERIC_KERNELS) && linear_geglu_tc_supported(M, D, K))
+    return launch_linear_geglu_tc(x, w, bias, y, M, D, K, dtype, (cudaStream_t)cuda_stream);
+  return launch_linear_geglu_generic(x, w, bias, y, M, D, K, dtype, (cudaStream_t)cuda_stream);
+}
+
 int paid_geglu(const void* h, void* out, int64_t M, int32_t D, int32_t dtype, void* cuda_stream) {
   if (!h || !out) return fail(PAID_EINVAL, "paid_geglu: h and out must be non-NULL");
   if (M <= 0 || D <= 0 || D % 8) return fail(PAID_EINVAL, "paid_geglu: M > 0 and D a positive multiple of 8");

@@ -134,11 +134,12 @@ class FeedForward(nn.Module):
         self.out = nn.Linear(dim * 4, dim)
 
     def forward(self, x):
-        h = self.proj(x)
-        if h.is_cuda and h.dtype in (torch.float16, torch.bfloat16):
+        if _native(x):
+            # both Linears on libpaid_attn's tcgen05 GEMM, the GEGLU in the first one's epilogue (the (rows, 8C)
+            # intermediate never reaches HBM)
             from . import _cabi
-            return self.out(_cabi.geglu(h))          # one fused HBM-bound kernel instead of gelu + mul on strided halves
-        a, g = h.chunk(2, dim=-1)
+            return _cabi.linear(_cabi.linear_geglu(x, self.proj.weight, self.proj.bias), self.out.weight, self.out.bias)
+        a, g = self.proj(x).chunk(2, dim=-1)
         return self.out(a * F.gelu(g))
 
 
@@ -175,7 +176,13 @@ class Transformer2DModel(nn.Module):
         b, c, hh, ww = x.shape
         res = x
         h = group_norm(self.norm, x)
-        if self.linear_proj:
+        native = _native(x)
+        if native:
+            # channels-last feature map = (tokens, C) matrix: proj_in / proj_out (Linear, or 1x1 conv for SD1.5) are plain
+            # GEMMs on libpaid_attn's tcgen05 kernel
+            from . import _cabi
+            h = _cabi.linear(h.permute(0, 2, 3, 1).reshape(b, hh * ww, c), self.proj_in.weight.reshape(c, c), self.proj_in.bias)
+        elif self.linear_proj:
             h = self.proj_in(h.permute(0, 2, 3, 1).reshape(b, hh * ww, c))
         else:
             h = self.proj_in(h).permute(0, 2, 3, 1).reshape(b, hh * ww, c)
@@ -184,7 +191,9 @@ class Transformer2DModel(nn.Module):
         for blk in self.transformer_blocks:
             h, pending = blk(h, ctx, pending)
         h = h + pending
-        if self.linear_proj:
+        if native:
+            h = _cabi.linear(h, self.proj_out.weight.reshape(c, c), self.proj_out.bias).reshape(b, hh, ww, c).permute(0, 3, 1, 2)
+        elif self.linear_proj:
             h = self.proj_out(h).reshape(b, hh, ww, c).permute(0, 3, 1, 2)
         else:
             h = self.proj_out(h.reshape(b, hh, ww, c).permute(0, 3, 1, 2))

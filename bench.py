@@ -146,7 +146,11 @@ def attention_traffic(net, frames, n_aid, n_plain):
     p = os.path.join(ROOT, "profiles", "attn_traffic.json")
     if not os.path.exists(p):
         return None, None, "no ncu capture committed"
-    rows = {(r["S"], r["L"], r["heads"], r["mode"]): r for r in json.load(open(p))["rows"]}
+    table = json.load(open(p))
+    if table.get("kernel_source_sha") != attention_kernel_sha():
+        return None, None, ("the committed ncu capture (profiles/attn_traffic.json) was taken on a different build of the attention "
+                            "kernels (source hash mismatch): re-run tools/ncu_core.py + tools/attn_traffic.py")
+    rows = {(r["S"], r["L"], r["heads"], r["mode"]): r for r in table["rows"]}
     total = launches = alg = 0.0
     for g in net.attention_geometry():
         for mode, reps in (("interpolated", n_aid), ("plain", n_plain)):
@@ -158,6 +162,16 @@ def attention_traffic(net, frames, n_aid, n_plain):
             launches += reps
     return total / launches, alg / launches, (f"launch-weighted mean over {int(launches)} launches of one sequence; per-shape rows in "
                               "profiles/attn_traffic.json (ncu --set full, tools/ncu_core.py)")
+
+
+def attention_kernel_sha() -> str:
+    """Hash of the attention-kernel sources: profiles/attn_traffic.json is only valid for the build it was captured on."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("attn_tc.cu", "attn_dw.cu", "sm100_ptx.cuh", "paid_common.cuh"):
+        with open(os.path.join(ROOT, "attention_interpolation_diffusion_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def peaks():
@@ -222,23 +236,106 @@ def cpu_reference_frames_per_sec(model: str, frames: int, atype: str, denoise_st
     return frames / seq_s, cores, sample, {"t_aid_forward_s": t_aid, "t_plain_forward_s": t_plain}
 
 
+def _reference_layer_runner(model: str, frames: int, atype: str):
+    """(kind, geometry list, run(layer geometry, aid) -> seconds) for the reference arm.  kind "reference": the UNMODIFIED
+    processors of /root/reference/interpolation.py on the Attention stand-in (only where that tree exists: the build
+    container); kind "port": the oracle restatement of the same path (oracle/paid_oracle.py forward_chunked), which is what
+    runs on the GPU box.  One call = one whole attention layer: q/k/v projections, attention of ALL frames and ALL query
+    rows, output projection -- no row sampling."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import paid_oracle as O
+    from attention_interpolation_diffusion_b200.unet_harness import CONFIGS, UNetHarness
+    torch.set_num_threads(os.cpu_count())
+    with torch.device("meta"):
+        geo = UNetHarness(CONFIGS[model]).attention_geometry()
+    mode = O.MODE_OUTER if atype == "fused_outer" else O.MODE_INNER
+    coef = O.coefficients(frames, 4, 4)
+    cache = {}
+
+    def tensors(g):
+        key = (g["S"], g["L"], g["C"], g["Cc"], g["heads"], g["self_attn"])
+        if key not in cache:      # layers of one geometry share weights and inputs (the time does not depend on the values)
+            w = O.make_layer(g["C"], g["Cc"], g["heads"], seed=1)
+            x, ctx = O.make_inputs(frames, g["S"], g["C"], None if g["self_attn"] else g["L"], g["Cc"], seed=1)
+            cache[key] = (w, x, ctx)
+        return cache[key]
+
+    kind = "port"
+    ref_mod = None
+    if os.path.isdir("/root/reference") and os.environ.get("PAID_BENCH_FORCE_PORT") != "1":
+        try:
+            from gen_golden import RefAttention, import_reference
+            from gen_e2e_golden import StockProcessor
+            ref_mod = import_reference()
+            kind = "reference"
+        except Exception:      # the reference tree is not importable here: fall back to the restatement
+            ref_mod = None
+
+    def run(g, aid: bool) -> float:
+        w, x, ctx = tensors(g)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            if ref_mod is not None:
+                cls = ref_mod.OuterInterpolatedAttnProcessor if mode == O.MODE_OUTER else ref_mod.InnerInterpolatedAttnProcessor
+                proc = cls(size=frames, is_fused=True, original_attn=StockProcessor())
+                proc.coef = coef.clone()
+                if not aid:
+                    proc.deactivate()
+                proc(RefAttention(w), x, encoder_hidden_states=ctx)
+            elif aid:
+                O.forward_chunked(x, ctx, w, coef, mode, True, rows=512)
+            else:
+                O.forward_chunked(x, ctx, w, coef, O.MODE_PLAIN, False, rows=512)
+        return time.perf_counter() - t0
+
+    return kind, geo, run
+
+
 def run_reference_arm(args):
+    """Reference arm: the reference's CPU implementation of the path on the box's host cores.  It cannot run K whole
+    sequences inside a few minutes (one SDXL sequence is about 1.3 hours of CPU attention), so the K timed steps
+    PARTITION one full pass over the attention stack: step k runs the layers k, k + K, k + 2K, ... of the UNet's 140 (32)
+    attention layers, each once interpolated (AID) and once deactivated (plain), complete (all frames, all rows).  Summed
+    over the steps that is exactly one AID forward and one plain forward of the attention stack, measured; the sequence
+    time is n_aid * T_aid + n_plain * T_plain (the only extrapolation: x forwards per sequence, and x frames / 7 when the
+    sequence has more than 7 frames -- the reference's cost per frame does not depend on the batch).  ms_per_step is the
+    measured wall time of a step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     frames = args.frames or FRAMES_PER_GPU * args.gpus
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, cores, sample, _ = cpu_reference_frames_per_sec(args.model, frames, args.atype, args.denoise_steps,
-                                                           budget_rows=128)
-        if i >= args.warmup:
-            vals.append(v)
-    value = statistics.mean(vals)
+    timed_frames = min(frames, 7)
+    kind, geo, run = _reference_layer_runner(args.model, timed_frames, args.atype)
+    K, W = max(args.steps, 1), args.warmup
+    small = min(geo, key=lambda g: g["S"] * g["L"])
+    for _ in range(W):                                   # warm-up: thread pool, allocator, the cheapest layer
+        run(small, True), run(small, False)
+    t_aid = t_plain = 0.0
+    step_s = []
+    for k in range(K):
+        t0 = time.perf_counter()
+        for g in geo[k::K]:
+            t_aid += run(g, True)
+            t_plain += run(g, False)
+        step_s.append(time.perf_counter() - t0)
+    n_aid = int(args.denoise_steps * WARMUP_RATIO)
+    n_plain = 2 * args.denoise_steps - n_aid
+    seq_s = (n_aid * t_aid + n_plain * t_plain) * frames / timed_frames
+    value = frames / seq_s
+    cores = os.cpu_count()
+    sample = (f"{'unmodified reference processors' if kind == 'reference' else 'oracle port of the reference processors'}, attention "
+              f"stack only ({len(geo)} layers): every layer once interpolated + once deactivated, all {timed_frames} frames and all "
+              f"query rows, partitioned over the {K} timed steps = one measured AID forward ({t_aid:.1f} s) + one measured plain forward "
+              f"({t_plain:.1f} s); sequence = {n_aid} x AID + {n_plain} x plain forwards"
+              + (f" x {frames}/{timed_frames} frames" if frames != timed_frames else "") + " (the only extrapolation)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * frames / value, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * statistics.mean(step_s), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, frames),
-            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample,
+                             "t_aid_forward_s": t_aid, "t_plain_forward_s": t_plain, "measured_s": sum(step_s),
+                             "sequence_s_extrapolated": seq_s},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -278,12 +375,16 @@ def run_own_arm(args):
     net = build_unet(args.model, dev, dtype, seed=1002)
     shard = FrameShard(rank, world, frames, None) if world > 1 else None
     pipe = InterpolationPipeline(net, shard=shard, use_cuda_graphs=not args.no_graphs)
-    if args.ip_tokens:
-        torch.manual_seed(1002)
-        pipe.load_aid_ip_adapter(num_tokens=args.ip_tokens, scale=1.0, t=None, is_fused=True, early=args.atype, size=frames,
-                                 alpha=4, beta=4)
-    else:
-        pipe.load_aid(t=None, is_fused=True, atype=args.atype, size=frames, alpha=4, beta=4)
+
+    def install(p_):
+        if args.ip_tokens:
+            torch.manual_seed(1002)
+            p_.load_aid_ip_adapter(num_tokens=args.ip_tokens, scale=1.0, t=None, is_fused=True, early=args.atype, size=frames,
+                                   alpha=4, beta=4)
+        else:
+            p_.load_aid(t=None, is_fused=True, atype=args.atype, size=frames, alpha=4, beta=4)
+
+    install(pipe)
     host = make_host_inputs(net.cfg, dtype, args.ip_tokens)
     devin = {k: v.to(dev) for k, v in host.items()}
     kw = dict(size=frames, alpha=4.0, beta=4.0, num_inference_steps=args.denoise_steps, warmup_ratio=WARMUP_RATIO)
@@ -340,6 +441,29 @@ def run_own_arm(args):
     k_ms, k_launches, k_flops = _cabi.profile_read(reset=True)
     pipe.use_cuda_graphs = not args.no_graphs
 
+    # frame-sharded run against the single-GPU run of the same sequence, once, outside the timed region (4 denoising steps)
+    sharded_parity = None
+    if world > 1:
+        kw_p = dict(kw, num_inference_steps=4)
+        local_out = pipe.interpolate(**devin, **kw_p)
+        parts = [torch.empty(len(ids), *local_out.shape[1:], dtype=local_out.dtype, device=dev) for ids in shard.shards]
+        for rk in range(world):
+            if rk == rank:
+                parts[rk].copy_(local_out)
+            dist.broadcast(parts[rk], src=rk)
+        if rank == 0:
+            gathered = shard.unshard(parts).float()
+            single = InterpolationPipeline(net, shard=None, use_cuda_graphs=not args.no_graphs)
+            install(single)
+            ref_out = single.interpolate(**devin, **kw_p).float()
+            rms = ref_out.pow(2).mean().sqrt()
+            sharded_parity = {"rel_rms": float((gathered - ref_out).pow(2).mean().sqrt() / rms),
+                              "max_abs_over_rms": float((gathered - ref_out).abs().max() / rms),
+                              "bit_identical": bool(torch.equal(gathered, ref_out)), "frames": frames, "denoise_steps": 4,
+                              "broadcasts_per_aid_forward": sum(1 for g_ in net.attention_geometry() if g_["self_attn"]),
+                              "how": "all ranks' frames gathered on rank 0 vs the unsharded run of the same sequence on GPU 0"}
+        dist.barrier()
+
     if rank == 0:
         peak_tf, _, peak_src = peaks()
         achieved = k_flops / (k_ms / 1000.0) / 1e12 if k_ms > 0 else None
@@ -358,9 +482,12 @@ def run_own_arm(args):
                            "kernel time / timed step; algorithmic flops per SURVEY.md 8d (fused-outer 6A, "
                            "fused-inner 4A, plain 2A; A = 2 N S L C)"}
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong" if (args.frames and world > 1) else "weak",
                 "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(args, frames),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
+        if sharded_parity is not None:
+            line["sharded_parity"] = sharded_parity
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, extra = cpu_reference_frames_per_sec(args.model, frames, args.atype, args.denoise_steps)
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample, **extra}

@@ -158,6 +158,13 @@ int paid_attn_project_kv(const PaidAttnParams* p, void* k_out, void* v_out, void
 int paid_linear(const void* x, const void* w, const void* bias, void* y, int64_t M, int32_t Nout, int32_t K,
                 int32_t dtype, uint32_t flags, void* cuda_stream);
 
+/* The feed-forward's first Linear with its GEGLU in the GEMM epilogue (diffusers FeedForward / GEGLU: proj = Linear(C, 8C),
+ * hidden, gate = proj(x).chunk(2); out = hidden * gelu(gate)):  w is (2 D, K) = [Wa ; Wg], bias (2 D,) = [ba ; bg] or NULL,
+ *   y (M, D) = (x Wa^T + ba) * gelu(x Wg^T + bg)        (exact erf GELU, fp32 before the one rounding to the 16-bit output)
+ * the (M, 2 D) intermediate never reaches HBM. */
+int paid_linear_geglu(const void* x, const void* w, const void* bias, void* y, int64_t M, int32_t D, int32_t K,
+                      int32_t dtype, uint32_t flags, void* cuda_stream);
+
 /* GEGLU of the transformer block's feed-forward (the caller next to the attention path):
  * h is (M, 2*D) = [a | g] per row (output of the first FF Linear), out (M, D) = a * gelu(g), exact (erf) GELU. */
 int paid_geglu(const void* h, void* out, int64_t M, int32_t D, int32_t dtype, void* cuda_stream);

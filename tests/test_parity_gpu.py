@@ -677,3 +677,27 @@ def test_interpolate_candidates_on_gpu(cabi):
         single = pipe.interpolate_single(t, **args, num_inference_steps=4).float().cpu()
         check(batch[i + 1], single[1], ("candidate", t), rel=2e-3)
         check(batch[0], single[0], ("start frame", t), rel=2e-3)
+
+
+def test_linear_geglu_against_torch(cabi):
+    """paid_linear_geglu (the feed-forward's first Linear with GEGLU in the GEMM epilogue, CTA-pair / 1-CTA / generic kernels)
+    against F.linear + chunk + a * gelu(g) in fp32 on the same 16-bit inputs."""
+    import torch.nn.functional as F
+    torch.manual_seed(4)
+    for (M, K, D), dt in (((7168, 1280, 5120), torch.float16), ((28672, 640, 2560), torch.float16), ((300, 64, 72), torch.float16),
+                          ((129, 320, 1280), torch.bfloat16), ((2, 128, 128), torch.float16), ((1000, 1280, 5120), torch.bfloat16)):
+        x = torch.randn(M, K, device="cuda").to(dt)
+        w = (torch.randn(2 * D, K, device="cuda") / K ** 0.5).to(dt)
+        b = torch.randn(2 * D, device="cuda").to(dt)
+        h = F.linear(x.float(), w.float(), b.float())
+        ref = (h[:, :D] * F.gelu(h[:, D:])).cpu()
+        for flags in (0, cabi.FLAG_GENERIC_KERNELS):
+            if flags and M * D * K > 2e10:
+                continue                     # the SIMT cross-check kernel is slow at the full feed-forward size
+            y = cabi.linear_geglu(x, w, b, flags=flags)
+            check(y.float().cpu(), ref, ("linear_geglu", M, K, D, dt, flags), rel=1e-3 if dt == torch.float16 else 8e-3,
+                  maxabs=MAXABS if dt == torch.float16 else 8 * MAXABS)
+        y = cabi.linear_geglu(x, w, None)
+        h = F.linear(x.float(), w.float())
+        check(y.float().cpu(), (h[:, :D] * F.gelu(h[:, D:])).cpu(), ("linear_geglu nobias", M, K, D), rel=1e-3 if dt == torch.float16 else 8e-3,
+              maxabs=MAXABS if dt == torch.float16 else 8 * MAXABS)
