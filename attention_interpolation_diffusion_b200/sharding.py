@@ -19,6 +19,7 @@ change over the denoising steps).  Deactivated (plain) calls need no communicati
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -56,7 +57,8 @@ class FrameShard:
     world_size: int
     num_frames: int
     group: Optional[object] = None
-    overlap: bool = True                       # broadcast on a side stream (False: on the compute stream, for A/B timing)
+    overlap: bool = field(default_factory=lambda: os.environ.get("PAID_SHARD_OVERLAP", "1") != "0")
+    # ^ broadcast on a side stream (False / PAID_SHARD_OVERLAP=0: on the compute stream, for A/B timing)
     shards: List[List[int]] = field(init=False)
     frame_ids: List[int] = field(init=False)
 
@@ -123,8 +125,11 @@ class FrameShard:
             return None
         main = torch.cuda.current_stream(kv.device)
         side = self.side_stream(kv.device)
-        if ready_on_main:                       # the owner: its projection kernels were queued on the compute stream
-            side.wait_stream(main)
+        # Every rank forks the side stream HERE, at the layer that consumes the data.  The owner has to (its projection
+        # kernels were queued on the compute stream); a receiver must not post its receive earlier either: an NCCL kernel
+        # spins on the GPU until its peer arrives, and 70 receives posted at the start of the forward kept ~8 % of the SMs
+        # busy-waiting through the whole forward (profiles/r2_shard_timing.jsonl: 85.9 ms instead of 79.7 per AID forward).
+        side.wait_stream(main)
         with torch.cuda.stream(side):
             dist.broadcast(kv, src=self._src(), group=self.group)
             ev = torch.cuda.Event()

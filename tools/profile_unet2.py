@@ -13,7 +13,7 @@ pipe.load_aid(t=None, is_fused=True, atype="fused_outer", size=N, alpha=4, beta=
 lat = torch.randn(N, 4, 128, 128, device="cuda").half().contiguous(memory_format=torch.channels_last)
 ctx = torch.randn(N, 77, 2048, device="cuda").half()
 added = {"text_embeds": torch.randn(N, 1280, device="cuda").half(), "time_ids": torch.zeros(N, 6, device="cuda").half()}
-PAID = r"(attn_tc_kernel|linear_tc_pair_kernel|linear_tc_kernel|add_layer_norm_kernel|gn_stats_kernel|gn_apply_kernel|residual_bias_add_kernel|geglu_kernel|lerp_endpoints_kernel|attn_generic_kernel|linear_generic_kernel)"
+PAID = r"(attn_dw_kernel|attn_tc_kernel|linear_geglu_generic_kernel|linear_tc_pair_kernel|linear_tc_kernel|add_layer_norm_kernel|gn_stats_kernel|gn_apply_kernel|residual_bias_add_kernel|geglu_kernel|lerp_endpoints_kernel|attn_generic_kernel|linear_generic_kernel)"
 AT = r"(GeluCUDAKernelImpl|direct_copy_kernel|silu|MulFunctor|AddFunctor|CUDAFunctor_add|LayerNorm\w*|layer_norm\w*|GroupNorm\w*|RowwiseMoments\w*|CatArrayBatchedCopy\w*|upsample\w*)"
 for mode in ("plain", "aid"):
     pipe.deactivate_aid() if mode == "plain" else pipe.set_coefs(torch.linspace(0, 1, N))
