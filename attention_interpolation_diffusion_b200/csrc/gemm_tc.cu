@@ -7,7 +7,7 @@
 //
 // Persistent, warp-specialised: one CTA per SM walks the output tiles (n fastest, so concurrently running
 // CTAs share the same rows of x in L2).  warp 0 = TMA producer (4-stage ring), warp 1 = MMA issuer,
-// warps 2-5 = epilogue.  The TMEM accumulator is DOUBLE-BUFFERED (2 x BN columns): the epilogue of tile i
+// warps 2-9 = epilogue (two per TMEM lane quadrant, half of the columns each).  The TMEM accumulator is DOUBLE-BUFFERED (2 x BN columns): the epilogue of tile i
 // overlaps the main loop of tile i+1.  BN = 256 (SS-mode operand fetch per flop is half of a 128-wide tile:
 // the 1-CTA MMA is shared-memory-bandwidth bound) unless the output width is not a multiple of 256.
 // Up to three weight matrices that share the same input (q/k/v of a self-attention layer, k/v of a
@@ -22,6 +22,10 @@ namespace paid {
 namespace {
 
 constexpr int BM = 128, BK = 64;
+// warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: EIGHT epilogue warps -- two per TMEM lane quadrant, each draining half
+// of the accumulator columns.  With four, the GEGLU epilogue (two TMEM loads, 32 erf-GELUs and a store per 32 columns) took
+// longer than the K = 640 main loop of the 64x64-level feed-forward (tensor pipe 39 % busy, profiles/r2_ncu_gemm.txt).
+constexpr int kGemmThreads = 320;
 constexpr int A_BYTES = BM * BK * 2;
 
 struct GroupPtrs {
@@ -64,7 +68,7 @@ template <int BN> struct Cfg {
 // [n0, n0 + 128) of Wa and of Wg, so accumulator columns 0..127 hold a and 128..255 hold g of the SAME output columns and
 // the epilogue writes (a + ba) * gelu(g + bg): the feed-forward's first Linear and its GEGLU in one kernel.
 template <typename T, int BN, bool GEGLU>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                  const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
                  const GroupPtrs gp, long long M, int N, int K, int m_tiles, int n_tiles, int total_tiles) {
@@ -87,7 +91,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB0);
     for (int s = 0; s < ST; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 8); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) { ptx::tmem_alloc(tmem_slot, C::kTmemCols); ptx::tmem_relinquish(); }
@@ -149,6 +153,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;   // which half of the accumulator columns this warp drains
     int tc = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
       int group, n0; long long m0;
@@ -161,7 +166,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const long long row = m0 + quad * 32 + lane;
       if constexpr (GEGLU) {
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = half * 2; c < half * 2 + 2; ++c) {
           uint32_t ra[32], rg[32];
           ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * BN + c * 32, ra);
           ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * BN + 128 + c * 32, rg);
@@ -171,7 +176,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       } else {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         uint32_t r[32];
         ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * BN + c * 32, r);
         ptx::tmem_wait_ld();
@@ -215,7 +220,7 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap* tmB, const GroupPtrs& gp
   const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = (N + TILE_N - 1) / TILE_N;
   const int total = m_tiles * n_tiles * groups;
   dim3 grid(total < num_sms ? total : num_sms);
-  PAID_CUDA_CHECK(launch_pdl(kern, grid, dim3(192), Cfg<BN>::kSmemBytes, stream, tmA, tmB[0], tmB[1], tmB[2], gp, M, N, K,
+  PAID_CUDA_CHECK(launch_pdl(kern, grid, dim3(kGemmThreads), Cfg<BN>::kSmemBytes, stream, tmA, tmB[0], tmB[1], tmB[2], gp, M, N, K,
                              m_tiles, n_tiles, total));
   PAID_LAUNCH_CHECK("linear_tc_kernel");
   return PAID_OK;
@@ -232,7 +237,7 @@ constexpr int P_STAGE_BYTES = A_BYTES + 128 * BK * 2;  // per CTA: 128 rows of x
 constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256;
 
 template <typename T, bool GEGLU>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                       const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
                       const GroupPtrs gp, long long M, int N, int K, int m_tiles, int n_tiles, int total_tiles) {
@@ -254,7 +259,7 @@ linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB0);
     for (int s = 0; s < ST; ++s) { ptx::mbar_init(&full[s], 2); ptx::mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 8); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 16); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
@@ -318,6 +323,7 @@ linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else {
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;   // which half of the accumulator columns this warp drains
     int tc = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs, ++tc) {
       int group, n0; long long m0;
@@ -330,7 +336,7 @@ linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const long long row = m0 + rank * 128 + quad * 32 + lane;
       if constexpr (GEGLU) {
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = half * 2; c < half * 2 + 2; ++c) {
           uint32_t ra[32], rg[32];
           ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * 256 + c * 32, ra);
           ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * 256 + 128 + c * 32, rg);
@@ -340,7 +346,7 @@ linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
       } else {
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = half * 4; c < half * 4 + 4; ++c) {
         uint32_t r[32];
         ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * 256 + c * 32, r);
         ptx::tmem_wait_ld();
@@ -383,7 +389,7 @@ int launch_pair_t(const CUtensorMap& tmA, const CUtensorMap* tmB, const GroupPtr
   const int total = m_tiles * n_tiles * groups;
   int pairs = num_sms / 2;
   if (total < pairs) pairs = total;
-  PAID_CUDA_CHECK(launch_pdl_pairs(kern, dim3(2 * pairs), dim3(192), P_SMEM_BYTES, stream, tmA, tmB[0], tmB[1], tmB[2], gp,
+  PAID_CUDA_CHECK(launch_pdl_pairs(kern, dim3(2 * pairs), dim3(kGemmThreads), P_SMEM_BYTES, stream, tmA, tmB[0], tmB[1], tmB[2], gp,
                                    M, N, K, m_tiles, n_tiles, total));
   PAID_LAUNCH_CHECK("linear_tc_pair_kernel");
   return PAID_OK;
