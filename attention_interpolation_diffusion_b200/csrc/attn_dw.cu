@@ -1,44 +1,47 @@
 // Single-stream attention core (PLAIN = deactivated processor / stock attention, INNER = lerped endpoint K/V) on the
-// 5th-generation tensor cores, head_dim <= 64: a PERSISTENT kernel whose key tiles are split between TWO softmax
-// warpgroups by tile parity.
+// 5th-generation tensor cores, head_dim <= 64: a PERSISTENT kernel with TWO independent softmax warpgroups per CTA, each
+// owning one 128-row Q block of a 256-row item; the K / V tiles are staged once and feed both.
 //
 // Replaces the reference's stock attention of the deactivated processors (interpolation.py:581-584, 715-718: 75 of the
 // 100 UNet forwards of a sequence) and the inner-interpolated attention (interpolation.py:760-790).
 //
-// Why this shape (round-2 profile of the one-warpgroup kernel in attn_tc.cu, profiles/r2_softmax_stalls.txt): a softmax
-// warp spends ~40 % of a key tile in its MUFU.EX2 burst and ~60 % in latencies around it (barrier polls, TMEM load /
-// store round trips, the max chain), two such warps per scheduler leave the SFU pipe 35 % idle, and splitting a ROW
-// between two threads (the dropped SP = 2 experiment) only doubled the per-row overhead.  Here every thread still owns a
-// whole query row of a whole 64-key tile, but the tiles of a Q block alternate between two warpgroups:
-//   warpgroup b (b = 0, 1) handles key tiles j = b, b + 2, ...  of the item with its OWN score buffer S_b, its OWN
-//   fp32 accumulator acc_b and its OWN running (max, sum): two independent flash-attention streams over disjoint key
-//   subsets, merged once per item in the epilogue with the log-sum-exp rule (merge()).
-// That puts four softmax warps on every scheduler (2 CTAs per SM) without any per-tile exchange between them.
+// Why this shape.  The one-warpgroup kernel (attn_tc.cu) left the SFU pipe 35 % idle: a softmax warp spends ~40 % of a key
+// tile in its MUFU.EX2 burst and the rest in latencies around it (barrier polls, TMEM load / store round trips), and two
+// such warps per scheduler cannot cover each other.  Two warpgroups per CTA (two CTAs per SM) put four softmax warps on
+// every scheduler.  The first dual-warpgroup version of this file split the KEY tiles of one Q block between the
+// warpgroups by parity and merged the two partial attentions in the epilogue: the exchange cost ~3500 cycles per item
+// (15 % of a 16-tile item, and most of an L = 77 item: profiles/r2_dw_cycle_trace.log).  Here the warpgroups never
+// meet: warpgroup b runs a complete flash-attention stream (all key tiles) for Q block b of the item, with its own
+// MMA-issuing warp, score buffer, accumulator, running (max, sum) and epilogue.
 //
-//   warp 0        TMA producer: Q block (double-buffered across items), K / V tiles (64 keys) through a 4-stage ring
-//   warps 1, 2    tcgen05.mma issuers, one per softmax warpgroup: S_b = Q K_j^T (SS), acc_b += P_b V_j (A operand P from TMEM)
+//   warp 0        TMA producer: the two Q blocks of an item, K / V tiles (64 keys) through a 4-stage ring
+//   warps 1, 2    tcgen05.mma issuers, one per warpgroup: S_b = Q_b K_j^T (SS), acc_b += P_b V_j (A operand P from TMEM)
 //   warp 3        idle (gives its registers away)
-//   warps 4-7     softmax warpgroup 0 (even tiles), one thread per query row
-//   warps 8-11    softmax warpgroup 1 (odd tiles)
+//   warps 4-7     softmax warpgroup 0 (Q block 0 of the item), one thread per query row
+//   warps 8-11    softmax warpgroup 1 (Q block 1)
 // TMEM (256 columns): S_0 | S_1 | acc_0 | acc_1, 64 columns each; P_b overwrites the low 32 columns of S_b (packed 16-bit).
 //
 // Persistent: the grid is (at most) two CTAs per SM; CTA c walks the items c, c + grid, ... of the list
-// (frame, head, 128-row Q block), Q block fastest.  The producer and the issuer run ahead across item boundaries (next
-// Q block and K tiles are in shared memory, the next scores in TMEM, while the softmax warps are still in the epilogue of
-// the previous item), so the per-CTA prologue (barrier init, TMEM allocation, descriptor fetch, first-load latency)
-// is paid once per CTA, not once per Q block: that is what the L = 77 cross-attention calls were dominated by.
+// (frame, head, 256-row Q block pair), Q block pair fastest.  The producer and the issuers run ahead across item
+// boundaries (the next Q block lands while the softmax warps work on the last tile and the epilogue of the current one),
+// so the per-CTA prologue (barrier init, TMEM allocation, descriptor fetch, first-load latency) is paid once per CTA.
 //
 // Speculative reference maximum: a tile is exponentiated against the running reference m_ref BEFORE its own maximum is
 // known (the maximum is reduced alongside); only if some row's maximum exceeds m_ref by more than 2^8 (never, after the
-// first tile, for real attention logits) is the accumulator rescaled and the tile redone.  The exponentials therefore do
-// not wait for the max reduction, and only 32 scores + the packed P are live per thread (96 registers).
+// first tile, for real attention logits) is the accumulator rescaled and the tile redone.
+//
+// Exponentials on two pipes.  At head_dim 64 a 128 x 64 score tile costs the tensor pipe 256 cycles (Q K^T + P V) and the
+// SFU 512 (16 MUFU.EX2 per clock per SM): the kernel is SFU-bound at half of the tensor peak.  kPolyPairs of every 16
+// element pairs are therefore exponentiated on the FMA pipe instead (Cody-Waite: round to nearest integer with the
+// 1.5 * 2^23 trick, cubic minimax polynomial of 2^f on [-0.5, 0.5], relative error 7.5e-5 -- below the 16-bit rounding of
+// P, 4.9e-4 / 3.9e-3 -- exponent added in the integer domain), as packed f32x2 instructions.
 #include <cstdlib>
 #include <type_traits>
 
 #include "paid_common.cuh"
 #include "sm100_ptx.cuh"
 
-// PAID_DW_TRACE: cycle accounting of CTA 0 (debug builds only, tools/build_variant.sh): prints where the issuer thread and
+// PAID_DW_TRACE: cycle accounting of CTA 0 (debug builds only, tools/build_variant.sh): prints where the issuer threads and
 // one softmax thread per warpgroup spend their time
 #ifdef PAID_DW_TRACE
 #define TR_DECL(...) long long __VA_ARGS__
@@ -50,11 +53,15 @@
 #define TR_ADD(acc, a, b)
 #endif
 
+#ifndef PAID_DW_POLY_PAIRS
+#define PAID_DW_POLY_PAIRS 4   // of every 16 element pairs: 25 % of the exponentials leave the SFU
+#endif
+
 namespace paid {
 namespace {
 
 constexpr int D = 64;                    // head_dim of the tiles (smaller head_dim: zero-padded by the TMA unit, see attn_tc.cu)
-constexpr int BM = 128;                  // query rows per item
+constexpr int BM = 128;                  // query rows per warpgroup (one Q block)
 constexpr int BN = 64;                   // keys per tile
 constexpr int ST = 4;                    // K / V ring stages
 constexpr int Q_BYTES = BM * D * 2;      // 16 KB
@@ -64,12 +71,12 @@ constexpr int kRegsControl = 48, kRegsSoftmax = 96;   // 128 * 48 + 256 * 96 = 3
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t TMEM_S = 0, TMEM_ACC = 128;
 constexpr float kRescaleThreshold = 8.f;  // log2 units
-constexpr int kXchBytes = 2 * 2 * BM * 8;  // [item parity][warpgroup][row] (max, sum)
-constexpr int kSmemBytes = 1024 + 2 * Q_BYTES + ST * 2 * KV_BYTES + 512 + kXchBytes;
+constexpr int kPolyPairs = PAID_DW_POLY_PAIRS;
+constexpr int kSmemBytes = 1024 + 2 * Q_BYTES + ST * 2 * KV_BYTES + 512;
 
 struct DwArgs {
   int mode, fused, N, S, L, heads, head_dim, begin_frame, end_frame;
-  int q_tiles, total_items;
+  int q_pairs, total_items;
   float scale_log2;
   const float* coef;
   void* out;
@@ -80,15 +87,15 @@ struct DwArgs {
 };
 
 struct Barriers {
-  uint64_t q_full[2], q_empty[2];
-  uint64_t k_full[ST], k_empty[ST], v_full[ST], v_empty[ST];
-  uint64_t s_full[2], p_full[2];
-  uint64_t acc_final, acc_empty;
+  uint64_t q_full[2], q_empty[2];                              // per warpgroup: its Q block
+  uint64_t k_full[ST], k_empty[ST], v_full[ST], v_empty[ST];   // shared ring: every tile is consumed by both issuers
+  uint64_t s_full[2], p_full[2];                               // per warpgroup: scores ready / P written
+  uint64_t acc_final[2], acc_empty[2];                         // per warpgroup: P.V of the item landed / accumulator drained
   uint32_t tmem_slot;
 };
 static_assert(sizeof(Barriers) <= 512, "barrier block");
 
-// one work item: a 128-row Q block of one head of one frame and the K/V slots it attends to (in order)
+// one work item: two adjacent 128-row Q blocks of one head of one frame and the K/V slots they attend to (in order)
 struct Item {
   int n, head, row0;
   int nseg;       // 1 or 2 key segments
@@ -105,11 +112,11 @@ __device__ __forceinline__ int frame_of_order(int z, int N) {
 
 __device__ __forceinline__ Item decode_item(int idx, const DwArgs& a) {
   Item it;
-  const int qt = idx % a.q_tiles;
-  const int r = idx / a.q_tiles;
+  const int qp = idx % a.q_pairs;
+  const int r = idx / a.q_pairs;
   it.head = r % a.heads;
   it.n = frame_of_order(r / a.heads, a.N);
-  it.row0 = qt * BM;
+  it.row0 = qp * 2 * BM;
   const float c = a.mode == PAID_PLAIN ? 0.f : a.coef[it.n];
   const FramePlan p = make_frame_plan(a.mode, a.fused, it.n, a.begin_frame, a.end_frame, c);
   it.nseg = (p.use0 ? 1 : 0) + (p.use1 ? 1 : 0);
@@ -117,6 +124,9 @@ __device__ __forceinline__ Item decode_item(int idx, const DwArgs& a) {
   it.w = p.wA;
   return it;
 }
+
+// element pair p (0..15) of a 32-column half goes to the FMA pipe: kPolyPairs of 16, evenly spread
+__host__ __device__ constexpr bool pair_on_fma_pipe(int p) { return ptx::pair_on_fma_pipe(p, kPolyPairs); }
 
 // One 64-key score tile of one query row: P = 2^(scale_log2 * (s - m_ref)) written over S as packed 16-bit, row sum
 // added to l.  `first`: the accumulator of this warpgroup is still empty, m_ref becomes the tile's true maximum.
@@ -174,12 +184,14 @@ __device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t acc_addr,
       }
 #pragma unroll
       for (int e = 0; e < 32; e += 2) {
-        const float2 x = ptx::fma2(make_float2(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])), sl2v, negv);
+        float2 x = ptx::fma2(make_float2(__uint_as_float(sr[e]), __uint_as_float(sr[e + 1])), sl2v, negv);
+        if (pair_on_fma_pipe(e / 2)) x = ptx::exp2_poly2(x);
         sr[e] = __float_as_uint(x.x); sr[e + 1] = __float_as_uint(x.y);
       }
       TR_T(p2);
 #pragma unroll
-      for (int e = 0; e < 32; ++e) sr[e] = __float_as_uint(ptx::ex2v(__uint_as_float(sr[e])));
+      for (int e = 0; e < 32; ++e)
+        if (!pair_on_fma_pipe(e / 2)) sr[e] = __float_as_uint(ptx::ex2v(__uint_as_float(sr[e])));
       TR_T(p3);
 #pragma unroll
       for (int e = 0; e < 32; e += 4) {
@@ -238,11 +250,10 @@ attn_dw_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmV1, const DwArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                         // [2][128][64]
+  uint8_t* sQ = smem;                         // [2 warpgroups][128][64]
   uint8_t* sK = sQ + 2 * Q_BYTES;             // [ST][64][64]
   uint8_t* sV = sK + ST * KV_BYTES;           // [ST][64][64]
   Barriers* bar = reinterpret_cast<Barriers*>(sV + ST * KV_BYTES);
-  float2* xch = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bar) + 512);   // [2][2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -250,15 +261,14 @@ attn_dw_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK0); ptx::prefetch_tmap(&tmV0);
     for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(&bar->q_full[b], 1); ptx::mbar_init(&bar->q_empty[b], 2);   // both issuers are done with the Q block
-      ptx::mbar_init(&bar->s_full[b], 1); ptx::mbar_init(&bar->p_full[b], 4);   // one arrive per softmax warp
+      ptx::mbar_init(&bar->q_full[b], 1); ptx::mbar_init(&bar->q_empty[b], 1);   // the issuer's last Q K^T of the item
+      ptx::mbar_init(&bar->s_full[b], 1); ptx::mbar_init(&bar->p_full[b], 4);    // one arrive per softmax warp
+      ptx::mbar_init(&bar->acc_final[b], 1); ptx::mbar_init(&bar->acc_empty[b], 4);
     }
     for (int s = 0; s < ST; ++s) {
-      ptx::mbar_init(&bar->k_full[s], 1); ptx::mbar_init(&bar->k_empty[s], 1);
-      ptx::mbar_init(&bar->v_full[s], 1); ptx::mbar_init(&bar->v_empty[s], 1);
+      ptx::mbar_init(&bar->k_full[s], 1); ptx::mbar_init(&bar->k_empty[s], 2);   // both issuers have read the tile
+      ptx::mbar_init(&bar->v_full[s], 1); ptx::mbar_init(&bar->v_empty[s], 2);
     }
-    ptx::mbar_init(&bar->acc_final, 2);   // the P.V products of both issuers have landed
-    ptx::mbar_init(&bar->acc_empty, 8);   // the eight softmax warps have read the accumulators of the item
     ptx::fence_barrier_init();
   }
   if (warp == 1) { ptx::tmem_alloc(&bar->tmem_slot, kTmemCols); ptx::tmem_relinquish(); }
@@ -276,15 +286,17 @@ attn_dw_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == 0) {
       // ================================ TMA producer ================================
       // The whole warp walks the loops (warp-uniform control flow keeps the counters and addresses in uniform
-      // registers); one elected lane arms the barriers and issues the TMA loads.
+      // registers); one elected lane arms the barriers and issues the TMA loads.  A Q block that starts at or beyond
+      // row S (odd number of 128-row blocks) is zero-filled by the TMA unit; its warpgroup computes on zeros and stores nothing.
       int kc = 0, itc = 0;
       for (int idx = blockIdx.x; idx < a.total_items; idx += gridDim.x, ++itc) {
         const Item it = decode_item(idx, a);
-        const int qb = itc & 1;
-        ptx::mbar_wait(&bar->q_empty[qb], ((itc >> 1) & 1) ^ 1);
-        if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(&bar->q_full[qb], Q_BYTES);
-          ptx::tma_load_4d(sQ + qb * Q_BYTES, &tmQ, &bar->q_full[qb], 0, it.head, it.row0, it.n);
+        for (int b = 0; b < 2; ++b) {
+          ptx::mbar_wait(&bar->q_empty[b], (itc & 1) ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&bar->q_full[b], Q_BYTES);
+            ptx::tma_load_4d(sQ + b * Q_BYTES, &tmQ, &bar->q_full[b], 0, it.head, it.row0 + b * BM, it.n);
+          }
         }
         for (int g = 0; g < it.nseg; ++g) {
           const int slot = g == 0 ? it.slot0 : 1;
@@ -309,19 +321,18 @@ attn_dw_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     } else if (warp <= 2) {
       // ================================ MMA issuers =================================
-      // Warp 1 issues for warpgroup 0 (even key tiles), warp 2 for warpgroup 1 (odd tiles): S_b = Q K_j^T and
-      // acc_b += P_b V_j touch disjoint TMEM columns, so the two issue streams need no ordering between them, and
-      // neither softmax warpgroup waits behind the other's tile (one in-order issuer coupled them: r2c trace, 500 cycles
-      // of issue + 200 of barrier polls per tile on the path from P(j) to S(j + 2)).  Warp-uniform loops; one elected
-      // lane issues tcgen05.mma / commit.
+      // Warp 1 issues for warpgroup 0, warp 2 for warpgroup 1: S_b = Q_b K_j^T and acc_b += P_b V_j touch disjoint TMEM
+      // columns, so the two issue streams need no ordering between them and neither softmax warpgroup waits behind the
+      // other's tile.  Both read every K / V stage; a stage is released when both have committed it.  Warp-uniform loops;
+      // one elected lane issues tcgen05.mma / commit.
       const int b = warp - 1;
       constexpr int fmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
       constexpr uint32_t idesc_qk = ptx::make_idesc(BM, BN, fmt, 0);  // S = Q K^T : both operands K-major
       constexpr uint32_t idesc_pv = ptx::make_idesc(BM, D, fmt, 1);   // acc += P V : V is N(=d)-contiguous
-      const uint32_t q_addr = ptx::smem_u32(sQ), k_addr = ptx::smem_u32(sK), v_addr = ptx::smem_u32(sV);
+      const uint32_t q_addr = ptx::smem_u32(sQ) + b * Q_BYTES, k_addr = ptx::smem_u32(sK), v_addr = ptx::smem_u32(sV);
       const uint32_t s_t = tmem + TMEM_S + b * BN, acc_t = tmem + TMEM_ACC + b * D;
-      auto issue_qk = [&](int qb, int s) {
-        const uint64_t qd = ptx::make_smem_desc_sw128(q_addr + qb * Q_BYTES, 16, 1024);
+      auto issue_qk = [&](int s) {
+        const uint64_t qd = ptx::make_smem_desc_sw128(q_addr, 16, 1024);
         const uint64_t kd = ptx::make_smem_desc_sw128(k_addr + s * KV_BYTES, 16, 1024);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) ptx::mma_ss(s_t, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
@@ -333,55 +344,47 @@ attn_dw_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int idx = blockIdx.x; idx < a.total_items; idx += gridDim.x, ++itc) {
         const Item it = decode_item(idx, a);
         const int total_steps = it.nseg * tiles;
-        const int qb = itc & 1;
         TR_T(tq0);
-        ptx::mbar_wait(&bar->q_full[qb], (itc >> 1) & 1);
+        ptx::mbar_wait(&bar->q_full[b], itc & 1);
         TR_T(tq1); TR_ADD(tr_q, tq0, tq1);
-        if (b < total_steps) {
-          // scores of this issuer's first step (S_b is free: its earlier P.V products were issued before this point)
-          const int s = (kc + b) % ST;
-          ptx::mbar_wait(&bar->k_full[s], ((kc + b) / ST) & 1);
+        {
+          // scores of the first step (S_b is free: the P.V products of the previous item were issued before this point)
+          const int s = kc % ST;
+          ptx::mbar_wait(&bar->k_full[s], (kc / ST) & 1);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
-            issue_qk(qb, s);
+            issue_qk(s);
             ptx::tc_commit(&bar->s_full[b]);
             ptx::tc_commit(&bar->k_empty[s]);
-            if (b + 2 >= total_steps) ptx::tc_commit(&bar->q_empty[qb]);   // this issuer's last Q K^T of the item
-          }
-        } else {   // no key tile of this parity in the item (L <= 64, one segment): arrive in this issuer's place.  Not before
-                   // the previous item's epilogue, or the arrival would be counted in the previous item's acc_final phase.
-          if (itc > 0) ptx::mbar_wait(&bar->acc_empty, (itc - 1) & 1);
-          if (ptx::elect_one()) {
-            ptx::mbar_arrive(&bar->q_empty[qb]);
-            ptx::mbar_arrive(&bar->acc_final);
+            if (total_steps == 1) ptx::tc_commit(&bar->q_empty[b]);   // the last Q K^T of the item
           }
         }
-        for (int j = b; j < total_steps; j += 2) {
-          const int s = (kc + j) % ST, s2 = (kc + j + 2) % ST;
-          const bool more = j + 2 < total_steps;
+        for (int j = 0; j < total_steps; ++j) {
+          const int s = (kc + j) % ST, s2 = (kc + j + 1) % ST;
+          const bool more = j + 1 < total_steps;
           TR_T(t0);
           ptx::mbar_wait(&bar->v_full[s], ((kc + j) / ST) & 1);
           TR_T(t1);
-          if (more) ptx::mbar_wait(&bar->k_full[s2], ((kc + j + 2) / ST) & 1);
+          if (more) ptx::mbar_wait(&bar->k_full[s2], ((kc + j + 1) / ST) & 1);
           TR_T(t2);
           ptx::mbar_wait(&bar->p_full[b], pcnt & 1);
           ++pcnt;
           TR_T(t3); TR_ADD(tr_v, t0, t1); TR_ADD(tr_k, t1, t2); TR_ADD(tr_p, t2, t3);
           // the first P.V of an item overwrites acc_b: the epilogue of the previous item must have drained it
-          if (j == b && itc > 0) ptx::mbar_wait(&bar->acc_empty, (itc - 1) & 1);
+          if (j == 0 && itc > 0) ptx::mbar_wait(&bar->acc_empty[b], (itc - 1) & 1);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
 #pragma unroll
             for (int k = 0; k < BN / 16; ++k) {
               // 16 keys per MMA: 8 packed columns of P, 16 rows (2048 B) of the V tile
               const uint64_t vd = ptx::make_smem_desc_sw128(v_addr + s * KV_BYTES + k * 2048, 16, 1024);
-              ptx::mma_ts(acc_t, s_t + k * 8, vd, idesc_pv, j != b || k != 0);
+              ptx::mma_ts(acc_t, s_t + k * 8, vd, idesc_pv, j != 0 || k != 0);
             }
-            if (!more) ptx::tc_commit(&bar->acc_final);   // this issuer's P.V products of the item have landed
-            if (more) {                                   // S_b is free again (in order after the P.V above)
-              issue_qk(qb, s2);
-              ptx::tc_commit(&bar->s_full[b]);            // scores of step j + 2
-              if (j + 4 >= total_steps) ptx::tc_commit(&bar->q_empty[qb]);
+            if (!more) ptx::tc_commit(&bar->acc_final[b]);   // the P.V products of the item have landed
+            if (more) {                                      // S_b is free again (in order after the P.V above)
+              issue_qk(s2);
+              ptx::tc_commit(&bar->s_full[b]);               // scores of step j + 1
+              if (j + 2 >= total_steps) ptx::tc_commit(&bar->q_empty[b]);
             }
             ptx::tc_commit(&bar->v_empty[s]);
             if (more) ptx::tc_commit(&bar->k_empty[s2]);
@@ -402,13 +405,12 @@ attn_dw_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   } else {
     ptx::setmaxnreg_inc<kRegsSoftmax>();
     // ================================ softmax warpgroups ==========================
-    const int b = (warp - 4) >> 2;   // warpgroup: key tiles j = b, b + 2, ...
+    const int b = (warp - 4) >> 2;   // warpgroup = Q block of the item
     const int quad = warp & 3;       // TMEM lane quadrant of this warp
     const int r = quad * 32 + lane;  // query row within the Q block
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t s_addr = tmem + lane_base + TMEM_S + b * BN;
-    const uint32_t acc_self = tmem + lane_base + TMEM_ACC + b * D;
-    const uint32_t acc_other = tmem + lane_base + TMEM_ACC + (b ^ 1) * D;
+    const uint32_t acc_addr = tmem + lane_base + TMEM_ACC + b * D;
     const float sl2 = a.scale_log2;
     const int C = a.heads * a.head_dim;
     uint32_t scnt = 0;   // score tiles consumed so far by this warpgroup (s_full phase)
@@ -424,15 +426,15 @@ attn_dw_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const Item it = decode_item(idx, a);
       const int total_steps = it.nseg * tiles;
       float m_ref = -INFINITY, l = 0.f;
-      int i = b;                      // tile index inside the current segment
-      for (int j = b; j < total_steps; j += 2, i += 2) {
-        if (i >= tiles) i -= tiles;   // next segment (tiles >= 1; i < 2 * tiles always)
+      int i = 0;                      // tile index inside the current segment
+      for (int j = 0; j < total_steps; ++j, ++i) {
+        if (i == tiles) i = 0;        // next segment
         TR_T(t0);
         ptx::mbar_wait(&bar->s_full[b], scnt & 1);
         ++scnt;
         ptx::tc_fence_after();
         TR_T(t1);
-        softmax_tile<T>(s_addr, acc_self, a.L - i * BN, j == b, sl2, m_ref, l, trp);
+        softmax_tile<T>(s_addr, acc_addr, a.L - i * BN, j == 0, sl2, m_ref, l, trp);
         TR_T(t2);
         ptx::tc_fence_before();
         __syncwarp();
@@ -443,56 +445,37 @@ attn_dw_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #endif
       }
       TR_T(te0);
-      // ---- epilogue: merge the two warpgroups' partial attentions, each stores 32 of the 64 channels of the head ----
-      float2* x = xch + (itc & 1) * 2 * BM;
-      x[b * BM + r] = make_float2(m_ref, l);
-      ptx::named_bar_sync(1, 256);
-      const float2 o = x[(b ^ 1) * BM + r];
-      const float M = fmaxf(m_ref, o.x);                       // warpgroup 0 always has a tile: M is finite
-      const float e_self = ptx::ex2((m_ref - M) * sl2), e_other = ptx::ex2((o.x - M) * sl2);
+      // ---- epilogue: out = [out +] os * acc / l, the 64 channels of the head for this thread's query row ----
       const float os = a.out_scale * (a.out_frame_scale ? a.out_frame_scale[it.n] : 1.f) * it.w;
-      const float inv = os / (e_self * l + e_other * o.y);
-      const float cf_self = e_self * inv, cf_other = e_other * inv;
-      ptx::mbar_wait(&bar->acc_final, itc & 1);
+      const float inv = os / l;
+      const int row = it.row0 + b * BM + r;
+      T* dst = (T*)a.out + ((long long)it.n * a.S + row) * C + it.head * a.head_dim;
+      ptx::mbar_wait(&bar->acc_final[b], itc & 1);
       ptx::tc_fence_after();
-      float acc[32];
-      {
-        uint32_t t[32];
-        if (total_steps > b) {   // this warpgroup had at least one tile (CTA-uniform)
-          ptx::tmem_ld32(acc_self + b * 32, t);
-          ptx::tmem_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e] = cf_self * __uint_as_float(t[e]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e] = 0.f;
-        }
-        if (total_steps > (b ^ 1)) {
-          ptx::tmem_ld32(acc_other + b * 32, t);
-          ptx::tmem_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e] = fmaf(cf_other, __uint_as_float(t[e]), acc[e]);
-        }
-      }
-      // the accumulators are in registers: the issuer may overwrite them with the next item's first P.V
+      uint32_t t0[32], t1[32];
+      ptx::tmem_ld32(acc_addr, t0);
+      ptx::tmem_ld32(acc_addr + 32, t1);
+      ptx::tmem_wait_ld();
+      // the accumulator is in registers: the issuer may overwrite it with the next item's first P.V
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar->acc_empty);
-      const int row = it.row0 + r;
+      if (lane == 0) ptx::mbar_arrive(&bar->acc_empty[b]);
       if (row < a.S) {
-        T* dst = (T*)a.out + ((long long)it.n * a.S + row) * C + it.head * a.head_dim + b * 32;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          if (b * 32 + v * 8 >= a.head_dim) break;   // padded head_dim: columns head_dim..63 are zero and are not stored
-          if (a.accumulate) {                        // out += ...: the IP-Adapter second attention (CTA-uniform branch)
+        for (int v = 0; v < 8; ++v) {
+          if (v * 8 >= a.head_dim) break;   // padded head_dim: columns head_dim..63 are zero and are not stored
+          const uint32_t* t = v < 4 ? &t0[v * 8] : &t1[(v - 4) * 8];
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = inv * __uint_as_float(t[e]);
+          if (a.accumulate) {               // out += ...: the IP-Adapter second attention (CTA-uniform branch)
             const uint4 old = *reinterpret_cast<const uint4*>(dst + v * 8);
             const T* o8 = reinterpret_cast<const T*>(&old);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[v * 8 + e] += to_f32(o8[e]);
+            for (int e = 0; e < 8; ++e) o[e] += to_f32(o8[e]);
           }
           *reinterpret_cast<uint4*>(dst + v * 8) =
-              make_uint4(pack2<T>(acc[v * 8], acc[v * 8 + 1]), pack2<T>(acc[v * 8 + 2], acc[v * 8 + 3]),
-                         pack2<T>(acc[v * 8 + 4], acc[v * 8 + 5]), pack2<T>(acc[v * 8 + 6], acc[v * 8 + 7]));
+              make_uint4(pack2<T>(o[0], o[1]), pack2<T>(o[2], o[3]), pack2<T>(o[4], o[5]), pack2<T>(o[6], o[7]));
         }
       }
       TR_T(te1); TR_ADD(tr_epi, te0, te1);
@@ -532,7 +515,7 @@ bool attn_dw_supported(const CoreArgs& a) {
   if (disabled) return false;
   if (a.mode != PAID_PLAIN && a.mode != PAID_INNER) return false;
   if (a.head_dim > D || a.head_dim < 16 || a.head_dim % 8) return false;
-  const long long items = (long long)a.N * a.heads * ((a.S + BM - 1) / BM);
+  const long long items = (long long)a.N * a.heads * ((a.S + 2 * BM - 1) / (2 * BM));
   return items < (1ll << 30) &&
          !(((uintptr_t)a.q | (uintptr_t)a.k | (uintptr_t)a.v | (uintptr_t)a.out | (uintptr_t)a.k1 | (uintptr_t)a.v1) & 15);
 }
@@ -561,8 +544,8 @@ int launch_attn_dw(const CoreArgs& a, cudaStream_t stream) {
   }
   da.mode = a.mode; da.fused = a.fused; da.N = a.N; da.S = a.S; da.L = a.L; da.heads = a.heads; da.head_dim = hd;
   da.begin_frame = a.begin_frame; da.end_frame = a.end_frame;
-  da.q_tiles = (a.S + BM - 1) / BM;
-  da.total_items = a.N * a.heads * da.q_tiles;
+  da.q_pairs = (a.S + 2 * BM - 1) / (2 * BM);
+  da.total_items = a.N * a.heads * da.q_pairs;
   da.scale_log2 = a.scale * kLog2e;
   da.coef = a.coef; da.out = a.out;
   da.accumulate = a.accumulate; da.out_scale = a.out_scale; da.out_frame_scale = a.out_frame_scale;

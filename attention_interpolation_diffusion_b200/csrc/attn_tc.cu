@@ -29,9 +29,14 @@
 #include "paid_common.cuh"
 #include "sm100_ptx.cuh"
 
+#ifndef PAID_TC_POLY_PAIRS
+#define PAID_TC_POLY_PAIRS 0   // element pairs (of every 16) exponentiated on the FMA pipe instead of the SFU (ptx::exp2_poly2)
+#endif
+
 namespace paid {
 namespace {
 
+constexpr int kPolyPairs = PAID_TC_POLY_PAIRS;
 constexpr int D = 64;            // head_dim of the tiles.  A smaller head_dim (multiple of 8) runs zero-padded: the 4-D
                                  // tensor maps have extent head_dim in their innermost dimension and a 64-wide box, so
                                  // the TMA unit fills columns head_dim..63 of every Q/K/V tile with zeros (scores and
@@ -344,13 +349,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int h = 0; h < 2; ++h)
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            const float2 x = ptx::fma2(make_float2(__uint_as_float(sr[h][e]), __uint_as_float(sr[h][e + 1])), sl2v, negv);
+            float2 x = ptx::fma2(make_float2(__uint_as_float(sr[h][e]), __uint_as_float(sr[h][e + 1])), sl2v, negv);
+            if (ptx::pair_on_fma_pipe(e / 2, kPolyPairs)) x = ptx::exp2_poly2(x);
             sr[h][e] = __float_as_uint(x.x); sr[h][e + 1] = __float_as_uint(x.y);
           }
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int e = 0; e < 32; ++e) sr[h][e] = __float_as_uint(ptx::ex2v(__uint_as_float(sr[h][e])));
+          for (int e = 0; e < 32; ++e)
+            if (!ptx::pair_on_fma_pipe(e / 2, kPolyPairs)) sr[h][e] = __float_as_uint(ptx::ex2v(__uint_as_float(sr[h][e])));
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t pk[16];

@@ -55,6 +55,25 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
       : "l"(reinterpret_cast<uint64_t const&>(a)), "l"(reinterpret_cast<uint64_t const&>(b)));
   return d;
 }
+// 2^x for a pair of elements on the FMA / ALU pipes (no MUFU): x = j + f with j = round(x), f in [-0.5, 0.5];
+// 2^f by a cubic (minimax for the relative error, 7.5e-5); 2^j by adding j to the exponent field.  Inputs below -125 are
+// clamped (their true value is below the smallest normal number; the result is ~1e-38 instead of 0).
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  constexpr float kMagic = 12582912.f;   // 1.5 * 2^23: (x + kMagic) has round(x) in its low mantissa bits
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = add2(x, make_float2(kMagic, kMagic));
+  const float2 j = add2(t, make_float2(-kMagic, -kMagic));
+  const float2 f = fma2(j, make_float2(-1.f, -1.f), x);
+  float2 p = fma2(make_float2(0.05517166f, 0.05517166f), f, make_float2(0.24261112f, 0.24261112f));
+  p = fma2(p, f, make_float2(0.69326099f, 0.69326099f));
+  p = fma2(p, f, make_float2(0.99992807f, 0.99992807f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
+                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
+}
+// of the 16 element pairs of a 32-column half, `pairs` (evenly spread) take exp2_poly2 instead of MUFU.EX2
+__host__ __device__ constexpr bool pair_on_fma_pipe(int p, int pairs) { return (p + 1) * pairs / 16 != p * pairs / 16; }
+
 // named barrier among `nthreads` threads of the CTA (ids 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -10,6 +10,7 @@ worst = 0.0
 shapes = ((3, 130, 77, 2, 64), (5, 700, 333, 3, 64), (4, 257, 64, 1, 64), (3, 64, 5, 2, 40), (3, 1, 1, 1, 64), (3, 129, 65, 5, 16),
           (3, 200, 77, 2, 56), (7, 1024, 1024, 20, 64), (4, 300, 640, 2, 64), (7, 1024, 77, 20, 64), (2, 4096, 4096, 2, 64),
           (5, 300, 130, 3, 40), (3, 257, 128, 2, 64), (3, 257, 129, 2, 64), (3, 257, 192, 2, 64), (3, 257, 193, 2, 64))
+if os.environ.get("TRY_DW_TIMING_ONLY") == "1": shapes = ()
 for N, S, L, h, d in shapes:
     q, k, v = (torch.randn(N, T, h * d, device="cuda").half() for T in (S, L, L))
     if L == 640: k = k * torch.linspace(0.2, 6.0, L, device="cuda").view(1, L, 1).half()     # growing logits: rescale path
@@ -51,7 +52,8 @@ N = 7
 coef = torch.linspace(0, 1, N, device="cuda")
 for S, L, h in ((4096, 4096, 10), (1024, 1024, 20), (1024, 77, 20), (4096, 77, 10)):
     q, k, v = (torch.randn(N, T, h * 64, device="cuda").half() for T in (S, L, L))
-    for name, mode, fused, mult in (("plain", _cabi.PAID_PLAIN, False, 2), ("inner_fused", _cabi.PAID_INNER, True, 4)):
+    for name, mode, fused, mult in (("plain", _cabi.PAID_PLAIN, False, 2), ("inner_fused", _cabi.PAID_INNER, True, 4),
+                                    ("outer_fused", _cabi.PAID_OUTER, True, 6)):   # OUTER runs attn_tc.cu under both flags
         t0 = timeit(lambda: _cabi.attn_core(q, k, v, coef, h, mode, fused, flags=OLD))
         t1 = timeit(lambda: _cabi.attn_core(q, k, v, coef, h, mode, fused))
         tf = mult * 2.0 * N * S * L * h * 64 / t1 / 1e9
