@@ -27,6 +27,7 @@ EXPORTS = [
     "paid_attn_abi_version", "paid_attn_workspace_bytes", "paid_attn_core_workspace_bytes", "paid_attn_forward",
     "paid_attn_core", "paid_attn_project_endpoints", "paid_attn_project_kv", "paid_linear", "paid_attn_last_error",
     "paid_attn_launch_count", "paid_attn_last_kernel", "paid_attn_profile_enable", "paid_attn_profile_read",
+    "paid_attn_profile_rows",
     "paid_linear_geglu", "paid_geglu", "paid_add_layer_norm", "paid_group_norm_nhwc", "paid_group_norm_workspace_bytes",
     "paid_residual_bias_add",
 ]
@@ -45,6 +46,14 @@ class PaidAttnParams(C.Structure):
         ("k_pre", C.c_void_p), ("v_pre", C.c_void_p), ("kv_pre_broadcast", C.c_int32), ("reserved0", C.c_int32),
         ("kv_ext_ready_event", C.c_void_p),
     ]
+
+
+class PaidProfileRow(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("d", C.c_int64 * 4), ("launches", C.c_uint64),
+                ("total_ms", C.c_double), ("flops", C.c_double)]
+
+
+PROFILE_KINDS = {0: "attention", 1: "linear", 2: "linear_geglu"}
 
 
 class PaidCoreParams(C.Structure):
@@ -110,6 +119,8 @@ def load_library() -> C.CDLL:
     lib.paid_attn_profile_enable.argtypes = [C.c_int]
     lib.paid_attn_profile_read.restype = C.c_int
     lib.paid_attn_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.c_int]
+    lib.paid_attn_profile_rows.restype = C.c_int
+    lib.paid_attn_profile_rows.argtypes = [C.POINTER(PaidProfileRow), C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
     if lib.paid_attn_abi_version() != 2:
         raise RuntimeError("libpaid_attn.so ABI version mismatch")
     _lib = lib
@@ -138,6 +149,18 @@ def profile_read(reset: bool = True):
     _check(load_library().paid_attn_profile_read(C.byref(ms), C.byref(n), C.byref(fl), int(reset)),
            "paid_attn_profile_read")
     return ms.value, int(n.value), fl.value
+
+
+def profile_rows(reset: bool = True):
+    """Per (kernel kind, shape) rows of the launches since the last reset: dicts with kind, d (shape key, see
+    include/paid_attn.h), launches, ms, flops."""
+    lib = load_library()
+    n = C.c_uint64(0)
+    _check(lib.paid_attn_profile_rows(None, 0, C.byref(n), 0), "paid_attn_profile_rows")
+    rows = (PaidProfileRow * max(1, n.value))()
+    _check(lib.paid_attn_profile_rows(rows, n.value, C.byref(n), int(reset)), "paid_attn_profile_rows")
+    return [dict(kind=PROFILE_KINDS.get(r.kind, str(r.kind)), d=[int(v) for v in r.d], launches=int(r.launches), ms=r.total_ms,
+                 flops=r.flops) for r in rows[:n.value]]
 
 
 def _check(status: int, what: str):

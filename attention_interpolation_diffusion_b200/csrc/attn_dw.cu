@@ -501,9 +501,7 @@ int launch_t(const CUtensorMap* maps, const DwArgs& da, cudaStream_t stream) {
   PAID_CUDA_CHECK(ensure_kernel_configured((const void*)kern, kSmemBytes, &num_sms));
   const int slots = 2 * (num_sms > 0 ? num_sms : 148);
   dim3 grid(da.total_items < slots ? da.total_items : slots);
-  profile_mark_begin(stream);
   PAID_CUDA_CHECK(launch_pdl(kern, grid, dim3(kThreads), kSmemBytes, stream, maps[0], maps[1], maps[2], maps[3], maps[4], da));
-  profile_mark_end(stream);
   PAID_LAUNCH_CHECK("attn_dw_kernel");
   return PAID_OK;
 }

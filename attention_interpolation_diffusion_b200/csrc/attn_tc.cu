@@ -29,14 +29,9 @@
 #include "paid_common.cuh"
 #include "sm100_ptx.cuh"
 
-#ifndef PAID_TC_POLY_PAIRS
-#define PAID_TC_POLY_PAIRS 0   // element pairs (of every 16) exponentiated on the FMA pipe instead of the SFU (ptx::exp2_poly2)
-#endif
-
 namespace paid {
 namespace {
 
-constexpr int kPolyPairs = PAID_TC_POLY_PAIRS;
 constexpr int D = 64;            // head_dim of the tiles.  A smaller head_dim (multiple of 8) runs zero-padded: the 4-D
                                  // tensor maps have extent head_dim in their innermost dimension and a 64-wide box, so
                                  // the TMA unit fills columns head_dim..63 of every Q/K/V tile with zeros (scores and
@@ -349,15 +344,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int h = 0; h < 2; ++h)
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            float2 x = ptx::fma2(make_float2(__uint_as_float(sr[h][e]), __uint_as_float(sr[h][e + 1])), sl2v, negv);
-            if (ptx::pair_on_fma_pipe(e / 2, kPolyPairs)) x = ptx::exp2_poly2(x);
+            const float2 x = ptx::fma2(make_float2(__uint_as_float(sr[h][e]), __uint_as_float(sr[h][e + 1])), sl2v, negv);
             sr[h][e] = __float_as_uint(x.x); sr[h][e + 1] = __float_as_uint(x.y);
           }
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (!ptx::pair_on_fma_pipe(e / 2, kPolyPairs)) sr[h][e] = __float_as_uint(ptx::ex2v(__uint_as_float(sr[h][e])));
+          for (int e = 0; e < 32; ++e) sr[h][e] = __float_as_uint(ptx::ex2v(__uint_as_float(sr[h][e])));
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t pk[16];
@@ -439,10 +432,8 @@ int launch_t(const CUtensorMap* maps, const TcArgs& ta, cudaStream_t stream) {
   static_assert(SMEM_BYTES <= 232448, "shared memory per CTA");
   PAID_CUDA_CHECK(ensure_kernel_configured((const void*)kern, SMEM_BYTES, nullptr));
   dim3 grid((ta.S + QT * BM - 1) / (QT * BM), ta.heads, ta.N);
-  profile_mark_begin(stream);
   PAID_CUDA_CHECK(launch_pdl(kern, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, maps[0], maps[1], maps[2], maps[3], maps[4],
                              maps[5], maps[6], ta));
-  profile_mark_end(stream);
   PAID_LAUNCH_CHECK("attn_tc_kernel");
   return PAID_OK;
 }

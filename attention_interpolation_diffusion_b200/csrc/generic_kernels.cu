@@ -364,9 +364,7 @@ static int launch_attn_generic_t(const CoreArgs& a, cudaStream_t stream) {
   auto kern = attn_generic_kernel<T, DPL>;
   if (smem > 48 * 1024) PAID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((a.S + kRowsPerBlock - 1) / kRowsPerBlock, a.heads, a.N);
-  profile_mark_begin(stream);
   kern<<<grid, kWarps * 32, smem, stream>>>(a);
-  profile_mark_end(stream);
   PAID_LAUNCH_CHECK("attn_generic_kernel");
   return PAID_OK;
 }

@@ -103,53 +103,67 @@ static int validate(const PaidAttnParams* p, bool need_io) {
 
 static int linear(const void* x, const void* w, const void* bias, void* y, long long M, int Nout, int K, int dtype,
                   uint32_t flags, cudaStream_t stream) {
-  if (!(flags & PAID_FLAG_GENERIC_KERNELS) && linear_tc_supported(M, Nout, K))
-    return launch_linear_tc(x, w, bias, y, M, Nout, K, dtype, stream);
-  return launch_linear_generic(x, w, bias, y, M, Nout, K, dtype, stream);
+  profile_mark_begin(stream, PAID_PROFILE_LINEAR, M, Nout, K, 1, 2.0 * M * Nout * K);
+  const int st = (!(flags & PAID_FLAG_GENERIC_KERNELS) && linear_tc_supported(M, Nout, K))
+                     ? launch_linear_tc(x, w, bias, y, M, Nout, K, dtype, stream)
+                     : launch_linear_generic(x, w, bias, y, M, Nout, K, dtype, stream);
+  profile_mark_end(stream);
+  return st;
 }
 
 // up to three projections of the same input in one launch (q/k/v of self-attention, k/v of cross-attention)
 static int linear_grouped(const void* x, const void* const* w, void* const* y, int groups, long long M, int Nout, int K,
                           int dtype, uint32_t flags, cudaStream_t stream) {
-  if (!(flags & PAID_FLAG_GENERIC_KERNELS) && linear_tc_supported(M, Nout, K))
-    return launch_linear_tc_grouped(x, w, nullptr, y, groups, M, Nout, K, dtype, stream);
-  for (int g = 0; g < groups; ++g) {
-    int st = launch_linear_generic(x, w[g], nullptr, y[g], M, Nout, K, dtype, stream);
-    if (st != PAID_OK) return st;
+  profile_mark_begin(stream, PAID_PROFILE_LINEAR, M, Nout, K, groups, 2.0 * M * Nout * K * groups);
+  int st = PAID_OK;
+  if (!(flags & PAID_FLAG_GENERIC_KERNELS) && linear_tc_supported(M, Nout, K)) {
+    st = launch_linear_tc_grouped(x, w, nullptr, y, groups, M, Nout, K, dtype, stream);
+  } else {
+    for (int g = 0; g < groups && st == PAID_OK; ++g) st = launch_linear_generic(x, w[g], nullptr, y[g], M, Nout, K, dtype, stream);
   }
-  return PAID_OK;
+  profile_mark_end(stream);
+  return st;
 }
 
-// ---- measurement hook: CUDA events around the attention-core kernel ------------------------------
+// ---- measurement hook: CUDA events around the attention-core and GEMM kernels ----------------------
+struct ProfileRecord {
+  cudaEvent_t begin = nullptr, end = nullptr;
+  int kind = 0;            // PAID_PROFILE_ATTENTION / _LINEAR / _LINEAR_GEGLU
+  long long d[4] = {0, 0, 0, 0};
+  double flops = 0;
+};
 struct ProfileState {
   std::mutex mu;
   bool on = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> used, pool;
-  std::pair<cudaEvent_t, cudaEvent_t> current{nullptr, nullptr};
-  double alg_flops = 0;
+  std::vector<ProfileRecord> used;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+  ProfileRecord current;
 };
 static ProfileState& prof() {
   static ProfileState p;
   return p;
 }
-void profile_mark_begin(cudaStream_t stream) {
+void profile_mark_begin(cudaStream_t stream, int kind, long long d0, long long d1, long long d2, long long d3, double flops) {
   ProfileState& ps = prof();
   if (!ps.on) return;
   std::lock_guard<std::mutex> lk(ps.mu);
-  if (!ps.pool.empty()) { ps.current = ps.pool.back(); ps.pool.pop_back(); }
-  else if (cudaEventCreate(&ps.current.first) != cudaSuccess || cudaEventCreate(&ps.current.second) != cudaSuccess) {
-    ps.current = {nullptr, nullptr};
+  ProfileRecord r;
+  if (!ps.pool.empty()) { r.begin = ps.pool.back().first; r.end = ps.pool.back().second; ps.pool.pop_back(); }
+  else if (cudaEventCreate(&r.begin) != cudaSuccess || cudaEventCreate(&r.end) != cudaSuccess) {
+    ps.current = ProfileRecord{};
     return;
   }
-  cudaEventRecord(ps.current.first, stream);
+  r.kind = kind; r.d[0] = d0; r.d[1] = d1; r.d[2] = d2; r.d[3] = d3; r.flops = flops;
+  ps.current = r;
+  cudaEventRecord(r.begin, stream);
 }
 void profile_mark_end(cudaStream_t stream) {
   ProfileState& ps = prof();
-  if (!ps.on || !ps.current.first) return;
+  if (!ps.on || !ps.current.begin) return;
   std::lock_guard<std::mutex> lk(ps.mu);
-  cudaEventRecord(ps.current.second, stream);
+  cudaEventRecord(ps.current.end, stream);
   ps.used.push_back(ps.current);
-  ps.current = {nullptr, nullptr};
+  ps.current = ProfileRecord{};
 }
 static double algorithmic_flops(const CoreArgs& a) {
   const double A = 2.0 * a.N * a.S * a.L * a.heads * a.head_dim;
@@ -159,9 +173,9 @@ static double algorithmic_flops(const CoreArgs& a) {
 }
 
 static int core_dispatch(const CoreArgs& a, uint32_t flags, cudaStream_t stream) {
-  ProfileState& ps = prof();
-  const size_t before = ps.on ? ps.used.size() : 0;
   int st;
+  profile_mark_begin(stream, PAID_PROFILE_ATTENTION, a.S, a.L, (long long)a.heads * a.head_dim, 16 * a.mode + a.fused,
+                     algorithmic_flops(a));
   static std::atomic<bool> pad_rejected{false};  // a zero-padded head_dim needs a TMA box wider than the tensor
   const bool padded = a.head_dim % 64 != 0;
   if (!(flags & PAID_FLAG_GENERIC_KERNELS) && attn_tc_supported(a) && !(padded && pad_rejected.load())) {
@@ -177,10 +191,7 @@ static int core_dispatch(const CoreArgs& a, uint32_t flags, cudaStream_t stream)
     *last_kernel_slot() = "generic";
     st = launch_attn_generic(a, stream);
   }
-  if (ps.on && ps.used.size() > before) {  // the launcher bracketed its kernel with events
-    std::lock_guard<std::mutex> lk(ps.mu);
-    ps.alg_flops += algorithmic_flops(a);
-  }
+  profile_mark_end(stream);
   return st;
 }
 
@@ -230,24 +241,60 @@ int paid_attn_profile_enable(int on) {
   return PAID_OK;
 }
 
+static int profile_collect(std::vector<PaidProfileRow>& rows) {
+  ProfileState& ps = prof();
+  for (auto& r : ps.used) {
+    PAID_CUDA_CHECK(cudaEventSynchronize(r.end));
+    float t = 0;
+    PAID_CUDA_CHECK(cudaEventElapsedTime(&t, r.begin, r.end));
+    PaidProfileRow* row = nullptr;
+    for (auto& q : rows)
+      if (q.kind == r.kind && q.d[0] == r.d[0] && q.d[1] == r.d[1] && q.d[2] == r.d[2] && q.d[3] == r.d[3]) { row = &q; break; }
+    if (!row) {
+      PaidProfileRow q{};
+      q.kind = r.kind;
+      for (int i = 0; i < 4; ++i) q.d[i] = r.d[i];
+      rows.push_back(q);
+      row = &rows.back();
+    }
+    row->launches += 1; row->total_ms += t; row->flops += r.flops;
+  }
+  return PAID_OK;
+}
+static void profile_reset() {
+  ProfileState& ps = prof();
+  for (auto& r : ps.used) ps.pool.push_back({r.begin, r.end});
+  ps.used.clear();
+}
+
 int paid_attn_profile_read(double* total_ms, uint64_t* launches, double* alg_flops, int reset) {
   ProfileState& ps = prof();
   std::lock_guard<std::mutex> lk(ps.mu);
-  double ms = 0;
-  for (auto& ev : ps.used) {
-    PAID_CUDA_CHECK(cudaEventSynchronize(ev.second));
-    float t = 0;
-    PAID_CUDA_CHECK(cudaEventElapsedTime(&t, ev.first, ev.second));
-    ms += t;
-  }
+  std::vector<PaidProfileRow> rows;
+  int st = profile_collect(rows);
+  if (st != PAID_OK) return st;
+  double ms = 0, fl = 0;
+  uint64_t n = 0;
+  for (auto& q : rows)
+    if (q.kind == PAID_PROFILE_ATTENTION) { ms += q.total_ms; n += q.launches; fl += q.flops; }
   if (total_ms) *total_ms = ms;
-  if (launches) *launches = ps.used.size();
-  if (alg_flops) *alg_flops = ps.alg_flops;
-  if (reset) {
-    for (auto& ev : ps.used) ps.pool.push_back(ev);
-    ps.used.clear();
-    ps.alg_flops = 0;
-  }
+  if (launches) *launches = n;
+  if (alg_flops) *alg_flops = fl;
+  if (reset) profile_reset();
+  return PAID_OK;
+}
+
+int paid_attn_profile_rows(PaidProfileRow* out, uint64_t capacity, uint64_t* count, int reset) {
+  if (!count) return fail(PAID_EINVAL, "paid_attn_profile_rows: count is NULL");
+  ProfileState& ps = prof();
+  std::lock_guard<std::mutex> lk(ps.mu);
+  std::vector<PaidProfileRow> rows;
+  int st = profile_collect(rows);
+  if (st != PAID_OK) return st;
+  *count = rows.size();
+  if (out)
+    for (uint64_t i = 0; i < rows.size() && i < capacity; ++i) out[i] = rows[i];
+  if (reset && (out || capacity == 0)) profile_reset();
   return PAID_OK;
 }
 
@@ -275,9 +322,13 @@ int paid_linear_geglu(const void* x, const void* w, const void* bias, void* y, i
   if (!x || !w || !y) return fail(PAID_EINVAL, "paid_linear_geglu: x, w, y must be non-NULL");
   if (M <= 0 || D <= 0 || K <= 0) return fail(PAID_EINVAL, "paid_linear_geglu: sizes must be positive");
   if (dtype != PAID_F16 && dtype != PAID_BF16) return fail(PAID_EINVAL, "paid_linear_geglu: bad dtype");
-  if (!(flags & PAID_FLAG_GENERIC_KERNELS) && linear_geglu_tc_supported(M, D, K))
-    return launch_linear_geglu_tc(x, w, bias, y, M, D, K, dtype, (cudaStream_t)cuda_stream);
-  return launch_linear_geglu_generic(x, w, bias, y, M, D, K, dtype, (cudaStream_t)cuda_stream);
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  profile_mark_begin(stream, PAID_PROFILE_LINEAR_GEGLU, M, D, K, 1, 4.0 * M * D * K);
+  const int st = (!(flags & PAID_FLAG_GENERIC_KERNELS) && linear_geglu_tc_supported(M, D, K))
+                     ? launch_linear_geglu_tc(x, w, bias, y, M, D, K, dtype, stream)
+                     : launch_linear_geglu_generic(x, w, bias, y, M, D, K, dtype, stream);
+  profile_mark_end(stream);
+  return st;
 }
 
 int paid_geglu(const void* h, void* out, int64_t M, int32_t D, int32_t dtype, void* cuda_stream) {

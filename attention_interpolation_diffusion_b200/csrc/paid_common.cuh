@@ -156,9 +156,11 @@ struct CoreArgs {
 // launched on the current device (thread-safe).  Also returns the SM count of the current device.
 cudaError_t ensure_kernel_configured(const void* kernel, int smem_bytes, int* num_sms);
 
-// measurement hook (paid_attn_profile_*): called by the attention launchers immediately around the kernel launch
-void profile_mark_begin(cudaStream_t stream);
+// measurement hook (paid_attn_profile_*): called by paid_api.cu immediately around the attention and GEMM launchers
+// (kind: PAID_PROFILE_*; d0..d3: the shape key of include/paid_attn.h; flops: algorithmic flops of the launch)
+void profile_mark_begin(cudaStream_t stream, int kind, long long d0, long long d1, long long d2, long long d3, double flops);
 void profile_mark_end(cudaStream_t stream);
+
 
 // kernel launchers (each returns a PaidStatus)
 int launch_linear_generic(const void* x, const void* w, const void* bias, void* y, long long M, int Nout, int K,

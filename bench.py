@@ -438,7 +438,10 @@ def run_own_arm(args):
     _cabi.profile_enable(True)
     ms_eager = timed(step_dev, 1)
     _cabi.profile_enable(False)
-    k_ms, k_launches, k_flops = _cabi.profile_read(reset=True)
+    prof_rows = _cabi.profile_rows(reset=True)
+    attn_rows = [r for r in prof_rows if r["kind"] == "attention"]
+    k_ms, k_launches, k_flops = (sum(r["ms"] for r in attn_rows), sum(r["launches"] for r in attn_rows),
+                                 sum(r["flops"] for r in attn_rows))
     pipe.use_cuda_graphs = not args.no_graphs
 
     # frame-sharded run against the single-GPU run of the same sequence, once, outside the timed region (4 denoising steps)
@@ -485,6 +488,24 @@ def run_own_arm(args):
                            "after the timed region (the timed steps replay CUDA graphs); share_of_step = summed "
                            "kernel time / timed step; algorithmic flops per SURVEY.md 8d (fused-outer 6A, "
                            "fused-inner 4A, plain 2A; A = 2 N S L C)"}
+        # every tcgen05 kernel of the path, per shape, in situ (same eager sequence, same events)
+        modes = {0: "plain", 16: "outer_pure", 17: "outer_fused", 32: "inner_pure", 33: "inner_fused"}
+        in_situ = []
+        for r in sorted(prof_rows, key=lambda r: -r["ms"]):
+            d = r["d"]
+            shape = ({"S": d[0], "L": d[1], "C": d[2], "mode": modes.get(d[3], str(d[3]))} if r["kind"] == "attention"
+                     else {"M": d[0], "N": d[1], "K": d[2], "groups": d[3]})
+            tf = r["flops"] / (r["ms"] / 1000.0) / 1e12 if r["ms"] > 0 else None
+            in_situ.append({"kernel": r["kind"], **shape, "launches": r["launches"], "ms": round(r["ms"], 3),
+                            "avg_us": round(1000.0 * r["ms"] / max(r["launches"], 1), 2), "tflops": round(tf, 1) if tf else None,
+                            "frac": round(tf / peak_tf, 3) if tf else None})
+        gemm = [r for r in prof_rows if r["kind"] != "attention"]
+        g_ms, g_fl = sum(r["ms"] for r in gemm), sum(r["flops"] for r in gemm)
+        roofline["gemm"] = {"kernel": "projection / feed-forward GEMMs (linear_tc_pair_kernel, GEGLU epilogue)", "bound": "tensor",
+                            "achieved": g_fl / (g_ms / 1000.0) / 1e12 if g_ms > 0 else None, "peak": peak_tf, "unit": "TFLOP/s",
+                            "frac": g_fl / (g_ms / 1000.0) / 1e12 / peak_tf if g_ms > 0 else None,
+                            "launches": sum(r["launches"] for r in gemm), "share_of_step": g_ms / (ms / args.steps)}
+        roofline["in_situ_by_shape"] = in_situ
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong" if (args.frames and world > 1) else "weak",

@@ -210,6 +210,24 @@ const char* paid_attn_last_kernel(void);
 int paid_attn_profile_enable(int on);
 int paid_attn_profile_read(double* total_ms, uint64_t* launches, double* alg_flops, int reset);
 
+/* The same hook per kernel shape: while enabled, the projection / feed-forward GEMM launches are bracketed too, and
+ * paid_attn_profile_rows returns one row per distinct (kind, shape) since the last reset:
+ *   PAID_PROFILE_ATTENTION     d = {S, L, heads * head_dim, 16 * mode + fused}, flops = algorithmic flops (as above)
+ *   PAID_PROFILE_LINEAR        d = {M, Nout, K, weight groups in the launch},  flops = 2 M Nout K groups
+ *   PAID_PROFILE_LINEAR_GEGLU  d = {M, D, K, 1},                                flops = 4 M D K
+ * At most `capacity` rows are written to `out`; *count receives the number of rows that exist (call with out == NULL
+ * and capacity == 0 to size the array; that call does not reset). */
+enum { PAID_PROFILE_ATTENTION = 0, PAID_PROFILE_LINEAR = 1, PAID_PROFILE_LINEAR_GEGLU = 2 };
+typedef struct PaidProfileRow {
+  int32_t kind;
+  int32_t reserved;
+  int64_t d[4];
+  uint64_t launches;
+  double total_ms;
+  double flops;
+} PaidProfileRow;
+int paid_attn_profile_rows(PaidProfileRow* out, uint64_t capacity, uint64_t* count, int reset);
+
 #ifdef __cplusplus
 }
 #endif

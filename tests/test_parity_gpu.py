@@ -701,3 +701,36 @@ def test_linear_geglu_against_torch(cabi):
         h = F.linear(x.float(), w.float())
         check(y.float().cpu(), (h[:, :D] * F.gelu(h[:, D:])).cpu(), ("linear_geglu nobias", M, K, D), rel=1e-3 if dt == torch.float16 else 8e-3,
               maxabs=MAXABS if dt == torch.float16 else 8 * MAXABS)
+
+
+def test_profile_rows_tag_every_kernel_of_a_layer(cabi):
+    """paid_attn_profile_rows (the measurement hook bench.py's in-situ table is built from): one processor call on a
+    self-attention and one on a cross-attention layer produce rows for the grouped q/k/v GEMM, the single GEMMs and the
+    attention core, with the documented shape keys and algorithmic flops; disabled, nothing is recorded."""
+    N, S, C, h, L, Cc = 3, 256, 128, 2, 77, 96
+    coef = O.coefficients(N, 4, 4).cuda()
+    ws, wc = O.make_layer(C, C, h, seed=1), O.make_layer(C, Cc, h, seed=2)
+    x, ctx = O.make_inputs(N, S, C, L, Cc, seed=3)
+    g = lambda t: dev(t)
+    cabi.profile_rows(reset=True)
+    cabi.profile_enable(True)
+    try:
+        cabi.attn_forward(g(x), None, g(ws.wq), g(ws.wk), g(ws.wv), g(ws.wo), g(ws.bo), coef, h, cabi.PAID_OUTER, True)
+        cabi.attn_forward(g(x), g(ctx), g(wc.wq), g(wc.wk), g(wc.wv), g(wc.wo), g(wc.bo), coef, h, cabi.PAID_PLAIN, False)
+        cabi.linear_geglu(g(x).view(N * S, C), g(torch.randn(2 * 64, C)), None)
+    finally:
+        cabi.profile_enable(False)
+    rows = {(r["kind"], tuple(r["d"])): r for r in cabi.profile_rows(reset=True)}
+    M = N * S
+    expect = {("linear", (M, C, C, 3)): (1, 2.0 * M * C * C * 3),             # q/k/v of the self-attention layer, one launch
+              ("linear", (M, C, C, 1)): (3, 3 * 2.0 * M * C * C),             # two out-projections and the cross-attention to_q
+              ("linear", (N * L, C, Cc, 2)): (1, 2.0 * N * L * C * Cc * 2),   # k/v of the cross-attention layer
+              ("attention", (S, S, C, 16 * cabi.PAID_OUTER + 1)): (1, 6 * 2.0 * N * S * S * C),
+              ("attention", (S, L, C, 0)): (1, 2 * 2.0 * N * S * L * C),
+              ("linear_geglu", (M, 64, C, 1)): (1, 4.0 * M * 64 * C)}
+    assert set(rows) == set(expect), sorted(rows)
+    for key, (launches, flops) in expect.items():
+        r = rows[key]
+        assert r["launches"] == launches and r["ms"] > 0 and abs(r["flops"] - flops) <= 1e-6 * flops, (key, r)
+    cabi.attn_forward(g(x), None, g(ws.wq), g(ws.wk), g(ws.wv), g(ws.wo), g(ws.bo), coef, h, cabi.PAID_OUTER, True)
+    assert cabi.profile_rows(reset=True) == []
