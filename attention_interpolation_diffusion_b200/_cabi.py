@@ -191,6 +191,10 @@ def _dev_check(*tensors):
 
 
 def _stream(t: torch.Tensor):
+    # the library launches on the CURRENT device (tensor maps, kernel attributes and the launch itself are per device)
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                           "wrap the call in torch.cuda.device(tensor.device)")
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
