@@ -121,15 +121,21 @@ class InterpolationPipeline:
     MAX_GRAPHS = 6       # captured forwards kept alive (each owns a private memory pool): 3 per (shape, processor set)
 
     def __init__(self, unet: UNetHarness, shard: Optional[FrameShard] = None, use_cuda_graphs: bool = True,
-                 cache_static_kv: bool = True):
+                 cache_static_kv: bool = True, merge_plain_passes: bool = True):
         self.unet = unet
+        # After the warm-up steps the conditional and the unconditional pass of a step both run stock attention
+        # (sdxl:2245-2248): the reference still calls the UNet twice with n frames; here they run as ONE call with 2 n frames
+        # (every op of the UNet is per sample, so the results are the same rows), which halves the launches of those steps
+        # and doubles the rows of every GEMM.  Text-only processors on CUDA only (the IP-Adapter variants read per-frame
+        # state while deactivated).
+        self.merge_plain_passes = merge_plain_passes
         self.scheduler = DDIMScheduler()
         self.shard = shard
         self.use_cuda_graphs = use_cuda_graphs
         self.cache_static_kv = cache_static_kv
         self._graphs: dict = {}            # insertion-ordered: oldest first (LRU eviction)
         self._coef_buf: Optional[torch.Tensor] = None     # fp32 coefficients of the local frames, shared by all processors
-        self._kv_tag = [None]              # the pass whose cached cross-attention K/V the processors read ("cond" / "uncond")
+        self._kv_tag = [None]              # the pass whose cached cross-attention K/V the processors read ("cond" / "uncond" / "both")
         self.graph_kernel_launches = 0     # libpaid_attn kernels executed through graph replays
         self.load_aid()
 
@@ -224,7 +230,7 @@ class InterpolationPipeline:
         for _, proc in self._installed():
             proc.bind_coef_buffer(self._coef_buf)
 
-    def _refresh_static_kv(self, cond, uncond, uncond_uniform: bool, cond_endpoints):
+    def _refresh_static_kv(self, cond, uncond, uncond_uniform: bool, cond_endpoints, both=None):
         """K / V of the prompt embeddings of every cross-attention layer, once per sequence (SURVEY.md section 8f rank 1;
         the reference re-projects them in all 100 UNet calls, interpolation.py:623-624).  The unconditional pass carries
         the same negative prompt in every frame: one (L, C) K/V pair serves all frames (kv_broadcast)."""
@@ -232,13 +238,16 @@ class InterpolationPipeline:
             for _, m in self.unet._attention_modules().items():
                 m.paid_kv = None
             return
+        passes = [("cond", cond, False, cond_endpoints), ("uncond", uncond, uncond_uniform, None)]
+        if both is not None:
+            passes.append(("both", both, False, None))
         for name, m in self.unet._attention_modules().items():
             if not name.endswith("attn2.processor"):
                 continue
             proc = m.processor
             if m.paid_kv is None:
-                m.paid_kv = {"cond": {}, "uncond": {}}
-            for tag, ctx, uniform, ends in (("cond", cond, False, cond_endpoints), ("uncond", uncond, uncond_uniform, None)):
+                m.paid_kv = {"cond": {}, "uncond": {}, "both": {}}
+            for tag, ctx, uniform, ends in passes:
                 entry = m.paid_kv[tag]
                 entry.pop("reallocated", None)
                 proc.project_static(m, ctx, uniform, entry, ends)
@@ -259,13 +268,22 @@ class InterpolationPipeline:
         self._bind_coefs(coef, latents.device)
         if self.shard is not None:
             self.shard.static_endpoints = cond_endpoints
-        self._refresh_static_kv(cond, uncond, uncond_uniform, cond_endpoints if self.shard is not None else None)
+        n = latents.shape[0]
+        merge = (self.merge_plain_passes and latents.is_cuda and warmup_steps < num_inference_steps and
+                 all(type(p) in (OuterInterpolatedAttnProcessor, InnerInterpolatedAttnProcessor) for _, p in self._installed()))
+        both = torch.cat([cond, uncond]) if merge else None
+        added_both = None if (not merge or added_cond is None) else {k: torch.cat([added_cond[k], added_uncond[k]]) for k in added_cond}
+        self._refresh_static_kv(cond, uncond, uncond_uniform, cond_endpoints if self.shard is not None else None, both)
         for i, t in enumerate(self.scheduler.timesteps.tolist()):
             model_in = self.scheduler.scale_model_input(latents, t)
-            noise_text = self._forward(i < warmup_steps, "cond", model_in, t, cond, added_cond, graphs)
-            if graphs:
-                noise_text = noise_text.clone()      # the next replay may reuse the same static output
-            noise_uncond = self._forward(False, "uncond", model_in, t, uncond, added_uncond, graphs)
+            if merge and i >= warmup_steps:
+                out = self._forward(False, "both", torch.cat([model_in, model_in]), t, both, added_both, graphs)
+                noise_text, noise_uncond = out[:n], out[n:]
+            else:
+                noise_text = self._forward(i < warmup_steps, "cond", model_in, t, cond, added_cond, graphs)
+                if graphs:
+                    noise_text = noise_text.clone()      # the next replay may reuse the same static output
+                noise_uncond = self._forward(False, "uncond", model_in, t, uncond, added_uncond, graphs)
             noise = noise_uncond + guidance_scale * (noise_text - noise_uncond)
             latents = self.scheduler.step(noise, t, latents)
         return latents

@@ -139,10 +139,12 @@ def kernel_rooflines(net, frames, atype, peak_tf):
     return out
 
 
-def attention_traffic(net, frames, n_aid, n_plain):
+def attention_traffic(net, mix):
     """roofline.traffic: ncu DRAM bytes (read + write) per attention-core launch, averaged over the launch mix of one
     sequence, from the committed `ncu --set full` capture (profiles/attn_traffic.json: one row per SDXL attention-layer
-    class and mode at 7 frames; scaled linearly with the frame count).  None if no capture covers the geometry."""
+    class and mode at 7 frames; scaled linearly with the frame count).  None if no capture covers the geometry.
+    mix: (mode, UNet forwards of that kind per sequence, frames per forward) -- the merged conditional + unconditional
+    forwards after the warm-up steps carry twice the frames."""
     p = os.path.join(ROOT, "profiles", "attn_traffic.json")
     if not os.path.exists(p):
         return None, None, "no ncu capture committed"
@@ -153,7 +155,9 @@ def attention_traffic(net, frames, n_aid, n_plain):
     rows = {(r["S"], r["L"], r["heads"], r["mode"]): r for r in table["rows"]}
     total = launches = alg = 0.0
     for g in net.attention_geometry():
-        for mode, reps in (("interpolated", n_aid), ("plain", n_plain)):
+        for mode, reps, frames in mix:
+            if reps == 0:
+                continue
             r = rows.get((g["S"], g["L"], g["heads"], mode))
             if r is None:
                 return None, None, "ncu capture does not cover this geometry"
@@ -344,7 +348,8 @@ def workload_config(args, frames):
     name = {"sdxl": "SDXL 128x128 latent", "sd15": "SD1.5 64x64 latent", "tiny": "tiny test UNet"}[args.model]
     ip = f" + IP-Adapter image morphing ({args.ip_tokens} image tokens per frame)" if args.ip_tokens else ""
     return {"workload": f"{name}, {frames}-frame PAID (guide prompt){ip}, {args.atype} AID in all attention layers, "
-                        f"{args.denoise_steps} steps, warmup_ratio {WARMUP_RATIO}, CFG (2 UNet passes/step)",
+                        f"{args.denoise_steps} steps, warmup_ratio {WARMUP_RATIO}, CFG (conditional + unconditional UNet pass per "
+                        "step; after the warm-up steps both run stock attention and are batched into one call)",
             "frames": frames, "frames_per_gpu": frames // max(args.gpus, 1), "denoise_steps": args.denoise_steps,
             "parallelism": f"frame-sharded x{args.gpus}" if args.gpus > 1 else "single GPU",
             "l2": "working set (5.1 GB fp16 UNet weights + activations) is far larger than the 126 MB L2; no explicit flush"}
@@ -475,8 +480,11 @@ def run_own_arm(args):
         peak_tf, _, peak_src = peaks()
         achieved = k_flops / (k_ms / 1000.0) / 1e12 if k_ms > 0 else None
         by_shape = kernel_rooflines(net, frames // world, args.atype, peak_tf)
-        n_aid = int(args.denoise_steps * WARMUP_RATIO)
-        traffic, alg_bytes, traffic_how = attention_traffic(net, frames // world, n_aid, 2 * args.denoise_steps - n_aid)
+        n_aid, fl = int(args.denoise_steps * WARMUP_RATIO), frames // world
+        merged = pipe.merge_plain_passes and not args.ip_tokens      # the two plain passes of a post-warm-up step run as one
+        mix = ([("interpolated", n_aid, fl), ("plain", n_aid, fl), ("plain", args.denoise_steps - n_aid, 2 * fl)] if merged else
+               [("interpolated", n_aid, fl), ("plain", 2 * args.denoise_steps - n_aid, fl)])
+        traffic, alg_bytes, traffic_how = attention_traffic(net, mix)
         roofline = {"kernel": f"attention core ({_cabi.last_kernel()})", "bound": "tensor", "achieved": achieved,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None,
                     "peak_source": peak_src, "traffic": traffic, "traffic_unit": "bytes per launch",

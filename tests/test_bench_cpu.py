@@ -46,7 +46,7 @@ def test_committed_ncu_traffic_covers_the_headline_workload():
     from attention_interpolation_diffusion_b200.unet_harness import CONFIGS, UNetHarness
     with torch.device("meta"):
         net = UNetHarness(CONFIGS["sdxl"])
-    traffic, alg, how = bench.attention_traffic(net, 7, 25, 75)
+    traffic, alg, how = bench.attention_traffic(net, [("interpolated", 25, 7), ("plain", 25, 7), ("plain", 25, 14)])
     if traffic is None and "source hash mismatch" in how:
         import pytest
         pytest.skip("profiles/attn_traffic.json is stale for this build of the kernels (bench.py then reports traffic: null)")

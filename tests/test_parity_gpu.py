@@ -342,7 +342,7 @@ def test_pipeline_cuda_graph_replay_equals_eager(cabi):
     pipe = InterpolationPipeline(net, use_cuda_graphs=True)
     first = pipe.interpolate(**args)
     again = pipe.interpolate(**args)                       # second call: pure replays
-    assert pipe.graph_kernel_launches > 0 and len(pipe._graphs) == 3      # (AID, cond), (plain, cond), (plain, uncond)
+    assert pipe.graph_kernel_launches > 0 and len(pipe._graphs) == 3      # (AID, cond), (plain, uncond), (plain, both passes merged)
     assert torch.equal(first, again)
     check(first.float().cpu(), eager.float().cpu(), "graph replay vs eager", rel=1e-3)
 
@@ -734,3 +734,30 @@ def test_profile_rows_tag_every_kernel_of_a_layer(cabi):
         assert r["launches"] == launches and r["ms"] > 0 and abs(r["flops"] - flops) <= 1e-6 * flops, (key, r)
     cabi.attn_forward(g(x), None, g(ws.wq), g(ws.wk), g(ws.wv), g(ws.wo), g(ws.bo), coef, h, cabi.PAID_OUTER, True)
     assert cabi.profile_rows(reset=True) == []
+
+
+def test_merged_plain_passes_equal_separate_passes(cabi):
+    """After the warm-up steps the step loop runs the conditional and the unconditional pass as ONE UNet call with 2 n frames
+    (pipeline.merge_plain_passes).  Every op is per sample, so the denoised latents must equal those of the reference's
+    two calls per step up to the convolution library's choice of kernel for the other batch size; the cross-attention K/V
+    of the merged pass come from the per-sequence cache entry "both"."""
+    from attention_interpolation_diffusion_b200.pipeline import InterpolationPipeline
+    from attention_interpolation_diffusion_b200.unet_harness import build_unet
+    net = build_unet("tiny", "cuda", torch.float16, seed=5)
+    g = torch.Generator("cpu").manual_seed(11)
+    r = lambda *s: torch.randn(*s, generator=g).cuda().half()
+    args = dict(latent_start=r(1, 4, 16, 16), latent_end=r(1, 4, 16, 16), embeds_start=r(1, 77, 96), embeds_end=r(1, 77, 96),
+                negative_embeds=r(1, 77, 96), pooled_start=r(1, 1280), pooled_end=r(1, 1280), pooled_negative=r(1, 1280),
+                size=5, alpha=4.0, beta=4.0, num_inference_steps=6, warmup_ratio=0.5)
+    outs = {}
+    for merge in (False, True):
+        for graphs in (False, True):
+            pipe = InterpolationPipeline(net, use_cuda_graphs=graphs, merge_plain_passes=merge)
+            pipe.load_aid(t=None, is_fused=True, atype="fused_outer", size=5, alpha=4, beta=4)
+            outs[merge, graphs] = pipe.interpolate(**args).float().cpu()
+            if merge:
+                kinds = {k[1] for k in pipe._graphs}
+                assert kinds == ({"cond", "uncond", "both"} if graphs else set()), kinds
+    assert torch.isfinite(outs[True, True]).all()
+    assert torch.equal(outs[True, True], outs[True, False])           # graph replay == eager
+    check(outs[True, False], outs[False, False], "merged vs separate passes", rel=2e-3)
