@@ -84,6 +84,7 @@ struct DwArgs {
   float out_scale;
   const float* out_frame_scale;
   int per_frame0, per_frame1;  // slot K/V map has one matrix per frame (1) or a single shared matrix (0)
+  int wide;                    // output rows of a head start on 32-byte boundaries: 32-byte stores
 };
 
 struct Barriers {
@@ -462,20 +463,32 @@ attn_dw_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (lane == 0) ptx::mbar_arrive(&bar->acc_empty[b]);
       if (row < a.S) {
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          if (v * 8 >= a.head_dim) break;   // padded head_dim: columns head_dim..63 are zero and are not stored
-          const uint32_t* t = v < 4 ? &t0[v * 8] : &t1[(v - 4) * 8];
-          float o[8];
+        for (int v = 0; v < 4; ++v) {       // 16 channels per step
+          if (v * 16 >= a.head_dim) break;  // padded head_dim: columns head_dim..63 are zero and are not stored
+          const uint32_t* t = v < 2 ? &t0[v * 16] : &t1[(v - 2) * 16];
+          const bool both = v * 16 + 8 < a.head_dim;   // head_dim % 16 == 8: the last step has 8 channels
+          float o[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = inv * __uint_as_float(t[e]);
+          for (int e = 0; e < 16; ++e) o[e] = inv * __uint_as_float(t[e]);
           if (a.accumulate) {               // out += ...: the IP-Adapter second attention (CTA-uniform branch)
-            const uint4 old = *reinterpret_cast<const uint4*>(dst + v * 8);
-            const T* o8 = reinterpret_cast<const T*>(&old);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] += to_f32(o8[e]);
+            for (int q = 0; q < 2; ++q) {
+              if (q == 1 && !both) break;
+              const uint4 old = *reinterpret_cast<const uint4*>(dst + v * 16 + q * 8);
+              const T* o8 = reinterpret_cast<const T*>(&old);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[q * 8 + e] += to_f32(o8[e]);
+            }
           }
-          *reinterpret_cast<uint4*>(dst + v * 8) =
-              make_uint4(pack2<T>(o[0], o[1]), pack2<T>(o[2], o[3]), pack2<T>(o[4], o[5]), pack2<T>(o[6], o[7]));
+          uint32_t w[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w[e] = pack2<T>(o[2 * e], o[2 * e + 1]);
+          if (a.wide && both) {
+            ptx::st_global_256(dst + v * 16, w);
+          } else {
+            *reinterpret_cast<uint4*>(dst + v * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (both) *reinterpret_cast<uint4*>(dst + v * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
         }
       }
       TR_T(te1); TR_ADD(tr_epi, te0, te1);
@@ -547,6 +560,7 @@ int launch_attn_dw(const CoreArgs& a, cudaStream_t stream) {
   da.scale_log2 = a.scale * kLog2e;
   da.coef = a.coef; da.out = a.out;
   da.accumulate = a.accumulate; da.out_scale = a.out_scale; da.out_frame_scale = a.out_frame_scale;
+  da.wide = hd % 16 == 0 && !((uintptr_t)a.out & 31);
   return a.dtype == PAID_F16 ? launch_t<__half>(maps, da, stream) : launch_t<__nv_bfloat16>(maps, da, stream);
 }
 

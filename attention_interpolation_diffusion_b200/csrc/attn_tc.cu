@@ -76,6 +76,7 @@ struct TcArgs {
   float out_scale;
   const float* out_frame_scale;
   int per_frame[3];  // slot K/V map has one matrix per frame (1) or a single shared matrix (0)
+  int wide;          // output rows of a head start on 32-byte boundaries: 32-byte stores
 };
 
 struct Barriers {
@@ -412,11 +413,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
 #pragma unroll
-        for (int v = 0; v < 4; ++v)
-          if (h * 32 + v * 8 < a.head_dim)  // padded head_dim: columns head_dim..63 are zero and are not stored
-            *reinterpret_cast<uint4*>(dst + h * 32 + v * 8) =
-                make_uint4(pack2<T>(acc[v * 8], acc[v * 8 + 1]), pack2<T>(acc[v * 8 + 2], acc[v * 8 + 3]),
-                           pack2<T>(acc[v * 8 + 4], acc[v * 8 + 5]), pack2<T>(acc[v * 8 + 6], acc[v * 8 + 7]));
+        for (int v = 0; v < 2; ++v) {   // 16 channels per step; padded head_dim: columns head_dim..63 are zero and are not stored
+          if (h * 32 + v * 16 >= a.head_dim) break;
+          uint32_t w[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w[e] = pack2<T>(acc[v * 16 + 2 * e], acc[v * 16 + 2 * e + 1]);
+          const bool both = h * 32 + v * 16 + 8 < a.head_dim;   // head_dim % 16 == 8: the last step has 8 channels
+          if (a.wide && both) {
+            ptx::st_global_256(dst + h * 32 + v * 16, w);
+          } else {
+            *reinterpret_cast<uint4*>(dst + h * 32 + v * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (both) *reinterpret_cast<uint4*>(dst + h * 32 + v * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
       }
     }
   }
@@ -485,6 +494,7 @@ int launch_attn_tc(const CoreArgs& a, cudaStream_t stream) {
   ta.scale_log2 = a.scale * kLog2e;
   ta.coef = a.coef; ta.out = a.out;
   ta.accumulate = a.accumulate; ta.out_scale = a.out_scale; ta.out_frame_scale = a.out_frame_scale;
+  ta.wide = a.head_dim % 16 == 0 && !((uintptr_t)a.out & 31);
   const char* force = getenv("PAID_ATTN_QT");   // tests flip this between calls: not cached
   const bool single_tile = !(force && force[0] == '2');
   if (hd > 2 * D)

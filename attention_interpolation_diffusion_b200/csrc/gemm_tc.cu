@@ -31,28 +31,60 @@ constexpr int A_BYTES = BM * BK * 2;
 struct GroupPtrs {
   const void* bias[3];
   void* y[3];
+  int wide;   // every y is 32-byte aligned and N % 16 == 0: rows are written with 32-byte stores (whole DRAM sectors)
 };
+
+// 16 consecutive 16-bit outputs (8 packed words) of one row: one 32-byte store, or two 16-byte stores
+__device__ __forceinline__ void store16(void* dst, const uint32_t (&o)[8], bool wide) {
+  if (wide) {
+    ptx::st_global_256(dst, o);
+  } else {
+    reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// 32 accumulator columns of one row -> y (+ bias); columns >= N (ragged last tile, N % 8 == 0) are not written
+template <typename T>
+__device__ __forceinline__ void store_row32(T* __restrict__ dst, const uint32_t (&r)[32], const T* __restrict__ bias, int col0,
+                                            int N, bool wide) {
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {  // 16 columns per step
+    const int col = col0 + v * 16;
+    if (col >= N) break;
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f0 = __uint_as_float(r[v * 16 + 2 * j]), f1 = __uint_as_float(r[v * 16 + 2 * j + 1]);
+      if (bias) { f0 += to_f32(bias[col + 2 * j]); f1 += to_f32(bias[col + 2 * j + 1]); }
+      o[j] = pack2<T>(f0, f1);
+    }
+    if (col + 16 <= N) store16(dst + v * 16, o, wide);
+    else *reinterpret_cast<uint4*>(dst + v * 16) = make_uint4(o[0], o[1], o[2], o[3]);   // 8 columns left
+  }
+}
 
 // 32 output columns of a GEGLU tile: out = (a + ba) * gelu(g + bg); bias is (2 N,) = [ba ; bg] or NULL
 template <typename T>
 __device__ __forceinline__ void geglu_store(T* __restrict__ dst, const uint32_t (&ra)[32], const uint32_t (&rg)[32],
-                                            const T* __restrict__ bias, int col0, int N) {
+                                            const T* __restrict__ bias, int col0, int N, bool wide) {
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {  // 8 columns = 16 bytes per store
-    const int col = col0 + v * 8;
+  for (int v = 0; v < 2; ++v) {  // 16 columns per step
+    const int col = col0 + v * 16;
     if (col >= N) break;
-    uint32_t o[4];
+    uint32_t o[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a0 = __uint_as_float(ra[v * 8 + 2 * j]), a1 = __uint_as_float(ra[v * 8 + 2 * j + 1]);
-      float g0 = __uint_as_float(rg[v * 8 + 2 * j]), g1 = __uint_as_float(rg[v * 8 + 2 * j + 1]);
+    for (int j = 0; j < 8; ++j) {
+      float a0 = __uint_as_float(ra[v * 16 + 2 * j]), a1 = __uint_as_float(ra[v * 16 + 2 * j + 1]);
+      float g0 = __uint_as_float(rg[v * 16 + 2 * j]), g1 = __uint_as_float(rg[v * 16 + 2 * j + 1]);
       if (bias) {
         a0 += to_f32(bias[col + 2 * j]); a1 += to_f32(bias[col + 2 * j + 1]);
         g0 += to_f32(bias[N + col + 2 * j]); g1 += to_f32(bias[N + col + 2 * j + 1]);
       }
       o[j] = pack2<T>(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
     }
-    *reinterpret_cast<uint4*>(dst + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    if (col + 16 <= N) store16(dst + v * 16, o, wide);
+    else *reinterpret_cast<uint4*>(dst + v * 16) = make_uint4(o[0], o[1], o[2], o[3]);   // 8 columns left
   }
 }
 
@@ -172,7 +204,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * BN + 128 + c * 32, rg);
           ptx::tmem_wait_ld();
           const int col0 = n0 + c * 32;
-          if (row < M && col0 < N) geglu_store<T>(y + row * N + col0, ra, rg, bias, col0, N);
+          if (row < M && col0 < N) geglu_store<T>(y + row * N + col0, ra, rg, bias, col0, N, gp.wide != 0);
         }
       } else {
 #pragma unroll 1
@@ -182,20 +214,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::tmem_wait_ld();
         const int col0 = n0 + c * 32;
         if (row < M && col0 < N) {
-          T* dst = y + row * N + col0;
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {  // 8 columns = 16 bytes per store
-            const int col = col0 + v * 8;
-            if (col >= N) break;
-            uint32_t o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float f0 = __uint_as_float(r[v * 8 + 2 * j]), f1 = __uint_as_float(r[v * 8 + 2 * j + 1]);
-              if (bias) { f0 += to_f32(bias[col + 2 * j]); f1 += to_f32(bias[col + 2 * j + 1]); }
-              o[j] = pack2<T>(f0, f1);
-            }
-            *reinterpret_cast<uint4*>(dst + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
-          }
+          store_row32<T>(y + row * N + col0, r, bias, col0, N, gp.wide != 0);
         }
       }
       }
@@ -342,7 +361,7 @@ linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           ptx::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + ab * 256 + 128 + c * 32, rg);
           ptx::tmem_wait_ld();
           const int col0 = n0 + c * 32;
-          if (row < M && col0 < N) geglu_store<T>(y + row * N + col0, ra, rg, bias, col0, N);
+          if (row < M && col0 < N) geglu_store<T>(y + row * N + col0, ra, rg, bias, col0, N, gp.wide != 0);
         }
       } else {
 #pragma unroll 1
@@ -352,20 +371,7 @@ linear_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         ptx::tmem_wait_ld();
         const int col0 = n0 + c * 32;
         if (row < M && col0 < N) {
-          T* dst = y + row * N + col0;
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const int col = col0 + v * 8;
-            if (col >= N) break;  // ragged last tile (N is a multiple of 8, not necessarily of 256)
-            uint32_t o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float f0 = __uint_as_float(r[v * 8 + 2 * j]), f1 = __uint_as_float(r[v * 8 + 2 * j + 1]);
-              if (bias) { f0 += to_f32(bias[col + 2 * j]); f1 += to_f32(bias[col + 2 * j + 1]); }
-              o[j] = pack2<T>(f0, f1);
-            }
-            *reinterpret_cast<uint4*>(dst + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
-          }
+          store_row32<T>(y + row * N + col0, r, bias, col0, N, gp.wide != 0);
         }
       }
       }
@@ -416,6 +422,7 @@ int launch_linear_tc_grouped(const void* x, const void* const* w, const void* co
     gp.bias[g] = bias ? bias[s] : nullptr;
     gp.y[g] = y[s];
   }
+  gp.wide = Nout % 16 == 0 && !(((uintptr_t)gp.y[0] | (uintptr_t)gp.y[1] | (uintptr_t)gp.y[2]) & 31);
   const bool wide = Nout % 256 == 0;
   // CTA pairs whenever the 256-wide tiles are at least 5/6 full (640 = 2.5 tiles still beats the 1-CTA kernel)
   const bool pairs_ok = M >= 256 && Nout >= 256 && 6 * Nout >= 5 * 256 * ((Nout + 255) / 256);
@@ -445,6 +452,7 @@ int launch_linear_geglu_tc(const void* x, const void* w, const void* bias, void*
   if ((st = make_tmap_2d(&tmB[0], w, dtype, 2LL * D, K, K, 128)) != PAID_OK) return st;
   tmB[1] = tmB[2] = tmB[0];
   gp.bias[0] = bias; gp.y[0] = y;
+  gp.wide = D % 16 == 0 && !((uintptr_t)y & 31);
   static const bool no_pairs = getenv("PAID_NO_CTA_PAIRS") != nullptr;
   if (M >= 256 && D >= 128 && !no_pairs)
     return dtype == PAID_F16 ? launch_pair_t<__half, true>(tmA, tmB, gp, 1, M, D, K, stream)

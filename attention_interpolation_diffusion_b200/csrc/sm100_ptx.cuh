@@ -74,6 +74,13 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // of the 16 element pairs of a 32-column half, `pairs` (evenly spread) take exp2_poly2 instead of MUFU.EX2
 __host__ __device__ constexpr bool pair_on_fma_pipe(int p, int pairs) { return (p + 1) * pairs / 16 != p * pairs / 16; }
 
+// 32-byte global store (sm_100: 256-bit vector stores; dst 32-byte aligned): a whole DRAM sector per lane.  Epilogues in
+// which every lane owns a different output row wrote each sector as two 16-byte halves before: half the store
+// instructions, and the K = 640 projection GEMMs went from 0.044 to 0.034 ms (profiles/r2_bench_gemm_st256.jsonl).
+__device__ __forceinline__ void st_global_256(void* dst, const uint32_t (&o)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+               "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+}
 // named barrier among `nthreads` threads of the CTA (ids 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
