@@ -43,7 +43,7 @@ class PaidAttnParams(C.Structure):
         ("x", C.c_void_p), ("ctx", C.c_void_p), ("wq", C.c_void_p), ("wk", C.c_void_p), ("wv", C.c_void_p),
         ("wo", C.c_void_p), ("bo", C.c_void_p), ("coef", C.c_void_p), ("kv_ext", C.c_void_p),
         ("y", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
-        ("k_pre", C.c_void_p), ("v_pre", C.c_void_p), ("kv_pre_broadcast", C.c_int32), ("reserved0", C.c_int32),
+        ("k_pre", C.c_void_p), ("v_pre", C.c_void_p), ("kv_pre_broadcast", C.c_int32), ("plain_tail", C.c_int32),
         ("kv_ext_ready_event", C.c_void_p),
     ]
 
@@ -121,7 +121,7 @@ def load_library() -> C.CDLL:
     lib.paid_attn_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.c_int]
     lib.paid_attn_profile_rows.restype = C.c_int
     lib.paid_attn_profile_rows.argtypes = [C.POINTER(PaidProfileRow), C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
-    if lib.paid_attn_abi_version() != 2:
+    if lib.paid_attn_abi_version() != 3:
         raise RuntimeError("libpaid_attn.so ABI version mismatch")
     _lib = lib
     return lib
@@ -212,8 +212,11 @@ def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 
 def make_params(x, ctx, wq, wk, wv, wo, bo, coef, heads: int, mode: int, fused: bool, scale: Optional[float] = None,
                 begin_frame: Optional[int] = None, end_frame: Optional[int] = None, kv_ext=None, flags: int = 0,
-                y=None) -> PaidAttnParams:
+                y=None, plain_tail: int = 0) -> PaidAttnParams:
     N, S, Cdim = x.shape
+    N -= plain_tail                  # trailing classifier-free-guidance rows (PaidAttnParams.plain_tail)
+    if plain_tail < 0 or N <= 0:
+        raise ValueError(f"plain_tail={plain_tail} does not leave an interpolation sequence in a batch of {x.shape[0]}")
     L, Cc = (S, Cdim) if ctx is None else (ctx.shape[1], ctx.shape[2])
     p = PaidAttnParams()
     p.struct_size = C.sizeof(PaidAttnParams)
@@ -225,14 +228,17 @@ def make_params(x, ctx, wq, wk, wv, wo, bo, coef, heads: int, mode: int, fused: 
     p.end_frame = N - 1 if end_frame is None else end_frame
     p.x, p.ctx, p.wq, p.wk, p.wv, p.wo, p.bo = map(_ptr, (x, ctx, wq, wk, wv, wo, bo))
     p.coef, p.kv_ext, p.y = _ptr(coef), _ptr(kv_ext), _ptr(y)
+    p.plain_tail = plain_tail
     return p
 
 
 def attn_forward(x, ctx, wq, wk, wv, wo, bo, coef, heads: int, mode: int, fused: bool, scale=None,
                  begin_frame=None, end_frame=None, kv_ext=None, flags: int = 0, out=None, k_pre=None, v_pre=None,
-                 kv_pre_broadcast: bool = False, kv_ext_ready=None) -> torch.Tensor:
+                 kv_pre_broadcast: bool = False, kv_ext_ready=None, plain_tail: int = 0) -> torch.Tensor:
     """One processor call through ``paid_attn_forward``.  Tensors: x (N,S,C), ctx None|(N,L,Cc), weights as in
-    nn.Linear, coef fp32 (N,) on the device (None for plain mode).  ``k_pre`` / ``v_pre``: K / V of the context projected
+    nn.Linear, coef fp32 (N,) on the device (None for plain mode).  ``plain_tail``: the last ``plain_tail`` frames of x /
+    ctx / k_pre are the unconditional rows of a classifier-free-guidance batch and get stock attention (the first
+    ``N - plain_tail`` frames are the interpolation sequence; coef has that many entries).  ``k_pre`` / ``v_pre``: K / V of the context projected
     earlier with ``project_kv`` ((N,L,C), or (1,L,C) with ``kv_pre_broadcast``); ``kv_ext_ready``: a ``torch.cuda.Event``
     the stream waits for before the attention core (the endpoint K/V in ``kv_ext`` arrive on another stream)."""
     lib = load_library()
@@ -243,7 +249,8 @@ def attn_forward(x, ctx, wq, wk, wv, wo, bo, coef, heads: int, mode: int, fused:
     if coef is not None and coef.dtype != torch.float32:
         raise RuntimeError("coef must be fp32")
     y = torch.empty_like(x) if out is None else out
-    p = make_params(x, ctx, wq, wk, wv, wo, bo, coef, heads, mode, fused, scale, begin_frame, end_frame, kv_ext, flags, y)
+    p = make_params(x, ctx, wq, wk, wv, wo, bo, coef, heads, mode, fused, scale, begin_frame, end_frame, kv_ext, flags, y,
+                    plain_tail)
     if k_pre is not None:
         if ctx is None and k_pre.shape[1] != x.shape[1]:
             raise RuntimeError("k_pre of a self-attention call must have S tokens")

@@ -60,8 +60,9 @@ struct Workspace {
 static Workspace plan_workspace(const PaidAttnParams* p) {
   Workspace w{};
   const uint64_t es = 2;
-  uint64_t nsc = align256((uint64_t)p->N * p->S * p->C * es);
-  uint64_t nlc = align256((uint64_t)p->N * p->L * p->C * es);
+  const uint64_t frames = (uint64_t)p->N + (uint64_t)p->plain_tail;
+  uint64_t nsc = align256(frames * p->S * p->C * es);
+  uint64_t nlc = align256(frames * p->L * p->C * es);
   uint64_t off = 0;
   w.q = off; off += nsc;
   w.k = off; off += nlc;
@@ -81,6 +82,7 @@ static int validate(const PaidAttnParams* p, bool need_io) {
   if (p->N <= 0 || p->S <= 0 || p->L <= 0 || p->C <= 0 || p->Cc <= 0 || p->heads <= 0)
     return fail(PAID_EINVAL, "sizes must be positive (N=%d S=%d L=%d C=%d Cc=%d heads=%d)", p->N, p->S, p->L, p->C,
                 p->Cc, p->heads);
+  if (p->plain_tail < 0) return fail(PAID_EINVAL, "plain_tail=%d must not be negative", p->plain_tail);
   if (p->C % p->heads) return fail(PAID_EINVAL, "C=%d is not a multiple of heads=%d", p->C, p->heads);
   if (p->C % 8 || p->Cc % 8) return fail(PAID_EUNSUPPORTED, "C and Cc must be multiples of 8 (16-byte rows)");
   if (!p->ctx && (p->L != p->S || p->Cc != p->C))
@@ -91,6 +93,8 @@ static int validate(const PaidAttnParams* p, bool need_io) {
   if (!p->k_pre && (!p->wk || !p->wv)) return fail(PAID_EINVAL, "wk, wv must be non-NULL (or k_pre / v_pre given)");
   if (p->kv_pre_broadcast && (!p->k_pre || p->mode != PAID_PLAIN))
     return fail(PAID_EINVAL, "kv_pre_broadcast needs k_pre / v_pre and PLAIN mode");
+  if (p->plain_tail && p->kv_pre_broadcast)
+    return fail(PAID_EINVAL, "plain_tail needs per-frame k_pre / v_pre (kv_pre_broadcast must be 0)");
   if (p->mode != PAID_PLAIN) {
     if (!p->coef) return fail(PAID_EINVAL, "coef is NULL");
     if (!p->kv_ext && (p->begin_frame < 0 || p->begin_frame >= p->N || p->end_frame < 0 || p->end_frame >= p->N))
@@ -460,7 +464,8 @@ int paid_attn_forward(const PaidAttnParams* p, void* cuda_stream) {
   char* base = (char*)p->workspace;
   void* Q = base + ws.q; void* K = base + ws.k; void* V = base + ws.v; void* H = base + ws.h;
   const void* src = p->ctx ? p->ctx : p->x;
-  const long long MS = (long long)p->N * p->S, ML = (long long)p->N * p->L;
+  const long long NT = (long long)p->N + p->plain_tail;   // the projections run over the interpolation sequence + CFG rows
+  const long long MS = NT * p->S, ML = NT * p->L;
 
   // interpolation.py:613, 623-624
   if (p->k_pre) {  // K / V of a step-invariant context were projected once per sequence (paid_attn_project_kv)
@@ -493,6 +498,17 @@ int paid_attn_forward(const PaidAttnParams* p, void* cuda_stream) {
   if ((st = resolve_slots(a, p->mode == PAID_PLAIN ? nullptr : p->kv_ext, kx, vx, stream)) != PAID_OK) return st;
   // interpolation.py:627-664 / 760-790
   if ((st = core_dispatch(a, p->flags, stream)) != PAID_OK) return st;
+  if (p->plain_tail > 0) {  // the unconditional rows of the step: stock attention on frames [N, N + plain_tail)
+    const long long qoff = (long long)p->N * p->S * p->C * 2, koff = (long long)p->N * p->L * p->C * 2;
+    CoreArgs b{};
+    b.dtype = p->dtype; b.mode = PAID_PLAIN; b.fused = 0;
+    b.N = p->plain_tail; b.S = p->S; b.L = p->L; b.heads = p->heads; b.head_dim = a.head_dim;
+    b.scale = p->scale; b.begin_frame = 0; b.end_frame = p->plain_tail - 1;
+    b.q = (const char*)Q + qoff; b.k = (const char*)K + koff; b.v = (const char*)V + koff; b.out = (char*)H + qoff;
+    b.accumulate = 0; b.out_scale = 1.f; b.out_frame_scale = nullptr;
+    b.stride0 = (long long)p->L * p->C;
+    if ((st = core_dispatch(b, p->flags, stream)) != PAID_OK) return st;
+  }
   // interpolation.py:666-667
   return linear(H, p->wo, p->bo, p->y, MS, p->C, p->C, p->dtype, p->flags, stream);
 }

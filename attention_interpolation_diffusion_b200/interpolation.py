@@ -67,6 +67,8 @@ class InterpolatedAttnProcessor(nn.Module):
         self.activated = True
         self.shard = None            # optional sharding.FrameShard
         self.kernel_flags = 0        # _cabi.FLAG_* (tests use FLAG_GENERIC_KERNELS as a cross-check)
+        self.cfg_tail = 0            # frames appended to the batch that get stock attention in the same call: the step loop
+                                     # runs the unconditional pass of a warm-up step as the tail of the conditional one
         self.coef_device = None      # optional fp32 device buffer holding the coefficients of the LOCAL frames; the step
                                      # loop binds one buffer to every processor and rewrites it in place, so captured
                                      # CUDA graphs serve any schedule (bind_coef_buffer)
@@ -118,12 +120,14 @@ class InterpolatedAttnProcessor(nn.Module):
         st = static_kv(attn, encoder_hidden_states)
         if self.shard is not None:
             return self.shard.run(self, attn, x, encoder_hidden_states, w, static=st)
-        if x.shape[0] != self.size or self.coef.numel() != self.size:
-            raise ValueError(f"batch size {x.shape[0]} / {self.coef.numel()} coefficients != processor size {self.size} "
-                             "(the frames of one interpolation sequence must form the batch)")
+        if x.shape[0] - self.cfg_tail != self.size or self.coef.numel() != self.size:
+            raise ValueError(f"batch size {x.shape[0]} (of which {self.cfg_tail} guidance rows) / {self.coef.numel()} "
+                             f"coefficients != processor size {self.size} (the frames of one interpolation sequence must "
+                             "form the batch)")
         st = st or {}
         return _cabi.attn_forward(x, encoder_hidden_states, *w, self._coef_on(x.device), attn.heads, self.mode, self.is_fused,
-                                  attn.scale, flags=self.kernel_flags, k_pre=st.get("k"), v_pre=st.get("v"))
+                                  attn.scale, flags=self.kernel_flags, k_pre=st.get("k"), v_pre=st.get("v"),
+                                  plain_tail=self.cfg_tail)
 
     def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
                  attention_mask: Optional[torch.Tensor] = None, temb: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -121,7 +121,7 @@ class InterpolationPipeline:
     MAX_GRAPHS = 6       # captured forwards kept alive (each owns a private memory pool): 3 per (shape, processor set)
 
     def __init__(self, unet: UNetHarness, shard: Optional[FrameShard] = None, use_cuda_graphs: bool = True,
-                 cache_static_kv: bool = True, merge_plain_passes: bool = True):
+                 cache_static_kv: bool = True, merge_plain_passes: bool = True, merge_aid_passes: bool = True):
         self.unet = unet
         # After the warm-up steps the conditional and the unconditional pass of a step both run stock attention
         # (sdxl:2245-2248): the reference still calls the UNet twice with n frames; here they run as ONE call with 2 n frames
@@ -129,6 +129,9 @@ class InterpolationPipeline:
         # and doubles the rows of every GEMM.  Text-only processors on CUDA only (the IP-Adapter variants read per-frame
         # state while deactivated).
         self.merge_plain_passes = merge_plain_passes
+        # The warm-up steps batch the same way: the unconditional frames ride as the tail of the conditional call, the
+        # processors interpolate the first n frames and run stock attention on the last n (PaidAttnParams.plain_tail).
+        self.merge_aid_passes = merge_aid_passes and merge_plain_passes
         self.scheduler = DDIMScheduler()
         self.shard = shard
         self.use_cuda_graphs = use_cuda_graphs
@@ -239,8 +242,8 @@ class InterpolationPipeline:
                 m.paid_kv = None
             return
         passes = [("cond", cond, False, cond_endpoints), ("uncond", uncond, uncond_uniform, None)]
-        if both is not None:
-            passes.append(("both", both, False, None))
+        if both is not None:             # conditional + unconditional frames in one call (the interpolated ones need the endpoints)
+            passes.append(("both", both, False, cond_endpoints))
         for name, m in self.unet._attention_modules().items():
             if not name.endswith("attn2.processor"):
                 continue
@@ -269,15 +272,18 @@ class InterpolationPipeline:
         if self.shard is not None:
             self.shard.static_endpoints = cond_endpoints
         n = latents.shape[0]
-        merge = (self.merge_plain_passes and latents.is_cuda and warmup_steps < num_inference_steps and
-                 all(type(p) in (OuterInterpolatedAttnProcessor, InnerInterpolatedAttnProcessor) for _, p in self._installed()))
+        text_only = all(type(p) in (OuterInterpolatedAttnProcessor, InnerInterpolatedAttnProcessor) for _, p in self._installed())
+        merge_plain = self.merge_plain_passes and latents.is_cuda and text_only and warmup_steps < num_inference_steps
+        merge_aid = self.merge_aid_passes and latents.is_cuda and text_only and warmup_steps > 0
+        merge = merge_plain or merge_aid
         both = torch.cat([cond, uncond]) if merge else None
         added_both = None if (not merge or added_cond is None) else {k: torch.cat([added_cond[k], added_uncond[k]]) for k in added_cond}
         self._refresh_static_kv(cond, uncond, uncond_uniform, cond_endpoints if self.shard is not None else None, both)
         for i, t in enumerate(self.scheduler.timesteps.tolist()):
             model_in = self.scheduler.scale_model_input(latents, t)
-            if merge and i >= warmup_steps:
-                out = self._forward(False, "both", torch.cat([model_in, model_in]), t, both, added_both, graphs)
+            if (merge_aid and i < warmup_steps) or (merge_plain and i >= warmup_steps):
+                aid = i < warmup_steps
+                out = self._forward(aid, "both", torch.cat([model_in, model_in]), t, both, added_both, graphs, tail=n if aid else 0)
                 noise_text, noise_uncond = out[:n], out[n:]
             else:
                 noise_text = self._forward(i < warmup_steps, "cond", model_in, t, cond, added_cond, graphs)
@@ -288,14 +294,15 @@ class InterpolationPipeline:
             latents = self.scheduler.step(noise, t, latents)
         return latents
 
-    def _set_mode(self, aid: bool):
+    def _set_mode(self, aid: bool, tail: int = 0):
         for _, proc in self._installed():
             proc.activated = bool(aid)      # AID on: conditional pass of the first warmup_steps steps (sdxl:2245-2248, 2272)
+            proc.cfg_tail = tail if aid else 0   # unconditional frames appended to an interpolated call
 
-    def _forward(self, aid: bool, tag: str, sample, t, ctx, added, graphs: bool):
+    def _forward(self, aid: bool, tag: str, sample, t, ctx, added, graphs: bool, tail: int = 0):
         self._kv_tag[0] = tag
         if not graphs:
-            self._set_mode(aid)
+            self._set_mode(aid, tail)
             if self.shard is not None:
                 self.shard.begin_forward(sample.device)
             out = self.unet(sample, t, ctx, added)
@@ -303,10 +310,10 @@ class InterpolationPipeline:
                 self.shard.end_forward(sample.device)
             return out
         # the coefficient VALUES are not part of the key: they live in the shared device buffer (_bind_coefs)
-        key = (aid, tag, tuple(sample.shape), tuple(ctx.shape), sample.dtype)
+        key = (aid, tag, tail, tuple(sample.shape), tuple(ctx.shape), sample.dtype)
         g = self._graphs.pop(key, None)
         if g is None:
-            self._set_mode(aid)
+            self._set_mode(aid, tail)
             while len(self._graphs) >= self.MAX_GRAPHS:
                 self._graphs.pop(next(iter(self._graphs)))     # least recently used
             g = _GraphedForward(self.unet, sample, t, ctx, added, self.shard)

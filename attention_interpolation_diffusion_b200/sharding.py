@@ -173,8 +173,9 @@ class FrameShard:
         """Interpolated attention of the local frames (called by the text processors)."""
         from .interpolation import _device_coef
 
-        if x.shape[0] != self.local_frames:
-            raise ValueError(f"local batch {x.shape[0]} != shard size {self.local_frames}")
+        tail = getattr(proc, "cfg_tail", 0)    # guidance rows appended to the local frames (stock attention, same call)
+        if x.shape[0] - tail != self.local_frames:
+            raise ValueError(f"local batch {x.shape[0]} (of which {tail} guidance rows) != shard size {self.local_frames}")
         if proc.size != self.num_frames:
             raise ValueError(f"processor size {proc.size} != sequence length {self.num_frames}")
         wq, wk, wv, wo, bo = w
@@ -191,4 +192,4 @@ class FrameShard:
         return _cabi.attn_forward(
             x, encoder_hidden_states, wq, wk, wv, wo, bo, coef, attn.heads, proc.mode, proc.is_fused, attn.scale,
             begin_frame=bf, end_frame=ef, kv_ext=None if self.owns_endpoints else kv, flags=proc.kernel_flags,
-            k_pre=st.get("k"), v_pre=st.get("v"), kv_ext_ready=ev)
+            k_pre=st.get("k"), v_pre=st.get("v"), kv_ext_ready=ev, plain_tail=tail)

@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly (for ncu launch lists)")
+    ap.add_argument("--ncu-range", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off: the launch list of the timed steps only)")
     return ap.parse_args()
 
 
@@ -347,9 +348,12 @@ def run_reference_arm(args):
 def workload_config(args, frames):
     name = {"sdxl": "SDXL 128x128 latent", "sd15": "SD1.5 64x64 latent", "tiny": "tiny test UNet"}[args.model]
     ip = f" + IP-Adapter image morphing ({args.ip_tokens} image tokens per frame)" if args.ip_tokens else ""
+    cfg = ("CFG (conditional + unconditional UNet pass per step)" if args.ip_tokens else
+           "CFG (the conditional and the unconditional frames of a step run as one UNet call with 2 n frames: during the warm-up "
+           "steps the attention layers interpolate the first n and run stock attention on the last n, afterwards all run stock "
+           "attention)")
     return {"workload": f"{name}, {frames}-frame PAID (guide prompt){ip}, {args.atype} AID in all attention layers, "
-                        f"{args.denoise_steps} steps, warmup_ratio {WARMUP_RATIO}, CFG (conditional + unconditional UNet pass per "
-                        "step; after the warm-up steps both run stock attention and are batched into one call)",
+                        f"{args.denoise_steps} steps, warmup_ratio {WARMUP_RATIO}, {cfg}",
             "frames": frames, "frames_per_gpu": frames // max(args.gpus, 1), "denoise_steps": args.denoise_steps,
             "parallelism": f"frame-sharded x{args.gpus}" if args.gpus > 1 else "single GPU",
             "l2": "working set (5.1 GB fp16 UNet weights + activations) is far larger than the 126 MB L2; no explicit flush"}
@@ -423,7 +427,11 @@ def run_own_arm(args):
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = _cabi.launch_count() + pipe.graph_kernel_launches
+    if args.ncu_range:
+        torch.cuda.cudart().cudaProfilerStart()
     ms = timed(step_dev, args.steps)
+    if args.ncu_range:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = _cabi.launch_count() + pipe.graph_kernel_launches - launches0
     clocks = sampler.stop()
     value = frames * args.steps / (ms / 1000.0)

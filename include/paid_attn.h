@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PAID_ABI_VERSION 2
+#define PAID_ABI_VERSION 3
 
 typedef enum PaidStatus {
   PAID_OK = 0,
@@ -103,7 +103,12 @@ typedef struct PaidAttnParams {
   const void* k_pre;
   const void* v_pre;
   int32_t kv_pre_broadcast;
-  int32_t reserved0;
+  /* ---- ABI 3 ----
+   * Classifier-free-guidance rows: x, ctx (or k_pre / v_pre), y and the workspace carry N + plain_tail frames; frames
+   * [0, N) are the interpolation sequence (mode / fused / coef / endpoints as above), frames [N, N + plain_tail) get stock
+   * attention (PLAIN) in the same call -- the unconditional pass of the step (pipeline_interpolated_sdxl.py:2272-2293
+   * runs it as a second UNet call with AID switched off).  The projections run once over all rows.  0: none. */
+  int32_t plain_tail;
   /* cudaEvent_t (or NULL): the stream waits for it after the local projections and before the attention core -- the
    * endpoint K/V in kv_ext are being delivered on another stream (the NCCL broadcast of a frame-sharded sequence),
    * so the transfer overlaps the q/k/v projection of the local frames. */

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(cabi):
     assert set(names) == set(cabi.EXPORTS)
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.paid_attn_abi_version() == 2
+    assert lib.paid_attn_abi_version() == 3
 
 
 def test_struct_layout_matches_header(cabi):
@@ -45,6 +45,11 @@ def test_struct_layout_matches_header(cabi):
     assert lib.paid_attn_workspace_bytes(C.byref(p)) == 4 * 3 * 64 * 128 * 2
     p.mode = 2
     assert lib.paid_attn_workspace_bytes(C.byref(p)) == 6 * 3 * 64 * 128 * 2
+    p.mode, p.plain_tail = 1, 3          # classifier-free-guidance rows ride in the same call: workspace for N + plain_tail frames
+    assert lib.paid_attn_workspace_bytes(C.byref(p)) == 4 * 6 * 64 * 128 * 2
+    p.plain_tail = -1
+    assert lib.paid_attn_workspace_bytes(C.byref(p)) == 0 and "plain_tail" in cabi.last_error()
+    p.plain_tail = 0
     p.struct_size -= 8
     assert lib.paid_attn_workspace_bytes(C.byref(p)) == 0
     assert "ABI mismatch" in cabi.last_error()

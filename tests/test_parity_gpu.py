@@ -679,6 +679,32 @@ def test_interpolate_candidates_on_gpu(cabi):
         check(batch[0], single[0], ("start frame", t), rel=2e-3)
 
 
+def test_beta_prior_exploration_on_gpu(cabi):
+    """The exploration loop (exploration.BetaPriorExplorer, reference prior.py:119-199) on the CUDA step loop: every explored
+    frame equals the middle frame of the reference-style 3-frame ``interpolate_single`` at its t, and a round with
+    batch = 2 denoises its two candidates in one call.  Features: the flattened latents (CLIP is out of scope)."""
+    from attention_interpolation_diffusion_b200.exploration import BetaPriorExplorer
+    from attention_interpolation_diffusion_b200.pipeline import InterpolationPipeline
+    from attention_interpolation_diffusion_b200.unet_harness import build_unet
+    net = build_unet("tiny", "cuda", torch.float16, seed=3)
+    g = torch.Generator("cpu").manual_seed(78)
+    r = lambda *s: torch.randn(*s, generator=g).cuda().half()
+    args = dict(latent_start=r(1, 4, 16, 16), latent_end=r(1, 4, 16, 16), embeds_start=r(1, 77, 96), embeds_end=r(1, 77, 96),
+                negative_embeds=r(1, 77, 96), pooled_start=r(1, 1280), pooled_end=r(1, 1280), pooled_negative=r(1, 1280),
+                num_inference_steps=4)
+    pipe = InterpolationPipeline(net)
+    ex = BetaPriorExplorer(pipe, feature_fn=lambda fr: fr.flatten(1))
+    frames, features, ds, xs, alpha, beta = ex.explore_with_beta(exploration_size=5, batch=1, **args)
+    assert len(xs) == 5 and xs == sorted(xs) and xs[0] == 0.0 and xs[-1] == 1.0 and all(d > 0 for d in ds)
+    for f, t in zip(frames[1:-1], xs[1:-1]):
+        single = pipe.interpolate_single(t, **{k: v for k, v in args.items()})
+        check(f[0].float().cpu(), single[1].float().cpu(), ("explored frame", t), rel=2e-3)
+    frames2, _, ds2, xs2, _, _ = ex.explore_with_beta(exploration_size=5, batch=2, **args)
+    assert len(xs2) == 5 and xs2 == sorted(xs2) and len(set(xs2)) == 5
+    out = ex.generate_interpolation(interpolation_size=3, exploration_size=5, batch=2, **args)
+    assert out.shape == (3, 4, 16, 16) and torch.isfinite(out).all()
+
+
 def test_linear_geglu_against_torch(cabi):
     """paid_linear_geglu (the feed-forward's first Linear with GEGLU in the GEMM epilogue, CTA-pair / 1-CTA / generic kernels)
     against F.linear + chunk + a * gelu(g) in fp32 on the same 16-bit inputs."""
@@ -736,11 +762,45 @@ def test_profile_rows_tag_every_kernel_of_a_layer(cabi):
     assert cabi.profile_rows(reset=True) == []
 
 
-def test_merged_plain_passes_equal_separate_passes(cabi):
-    """After the warm-up steps the step loop runs the conditional and the unconditional pass as ONE UNet call with 2 n frames
-    (pipeline.merge_plain_passes).  Every op is per sample, so the denoised latents must equal those of the reference's
-    two calls per step up to the convolution library's choice of kernel for the other batch size; the cross-attention K/V
-    of the merged pass come from the per-sequence cache entry "both"."""
+def test_plain_tail_rows_equal_a_separate_plain_call(cabi):
+    """PaidAttnParams.plain_tail: the unconditional frames of a classifier-free-guidance step appended to the interpolation
+    sequence get stock attention inside the same call (projections over all rows, two attention-core launches).  Every
+    kernel of the call is row / frame independent, so the result is BIT-identical to the reference's two calls
+    (interpolated on the sequence, deactivated on the unconditional frames; pipeline_interpolated_sdxl.py:2245-2293)."""
+    N, T, S, C, h, L, Cc = 5, 5, 256, 128, 2, 77, 96
+    coef = O.coefficients(N, 4, 4).cuda()
+    for cross in (False, True):
+        w = O.make_layer(C, Cc if cross else C, h, seed=21)
+        x, ctx = O.make_inputs(N, S, C, L if cross else None, Cc, seed=22)
+        xu, ctxu = O.make_inputs(T, S, C, L if cross else None, Cc, seed=23)
+        W = [dev(t) for t in (w.wq, w.wk, w.wv, w.wo, w.bo)]
+        xa, xb = dev(x), dev(xu)
+        ca, cb = (dev(ctx), dev(ctxu)) if cross else (None, None)
+        both_x = torch.cat([xa, xb]).contiguous()
+        both_c = torch.cat([ca, cb]).contiguous() if cross else None
+        for mode, fused in ((cabi.PAID_OUTER, True), (cabi.PAID_OUTER, False), (cabi.PAID_INNER, True)):
+            y_seq = cabi.attn_forward(xa, ca, *W, coef, h, mode, fused)
+            y_unc = cabi.attn_forward(xb, cb, *W, None, h, cabi.PAID_PLAIN, False)
+            y = cabi.attn_forward(both_x, both_c, *W, coef, h, mode, fused, plain_tail=T)
+            assert torch.equal(y[:N], y_seq) and torch.equal(y[N:], y_unc), (cross, mode, fused)
+            ok, m = O.within_tolerance(y[:N].float().cpu(), O.forward_direct(x, ctx, w, O.coefficients(N, 4, 4), mode, fused))
+            assert ok, (cross, mode, fused, m)
+            if cross:       # K / V of the step-invariant prompts from the per-sequence cache (paid_attn_project_kv)
+                k_pre, v_pre = torch.empty(N + T, L, C, device="cuda", dtype=xa.dtype), torch.empty(N + T, L, C, device="cuda", dtype=xa.dtype)
+                cabi.project_kv(both_x, both_c, W[1], W[2], h, k_pre, v_pre)
+                y2 = cabi.attn_forward(both_x, both_c, *W, coef, h, mode, fused, plain_tail=T, k_pre=k_pre, v_pre=v_pre)
+                assert torch.equal(y2, y), (mode, fused)
+    with pytest.raises(ValueError):
+        cabi.attn_forward(xa, None, *W, coef, h, cabi.PAID_OUTER, True, plain_tail=N)
+
+
+def test_merged_passes_equal_separate_passes(cabi):
+    """The step loop runs the conditional and the unconditional pass of a step as ONE UNet call with 2 n frames: after the
+    warm-up steps both run stock attention (pipeline.merge_plain_passes); during the warm-up steps the processors
+    interpolate the first n frames and run stock attention on the last n (pipeline.merge_aid_passes, plain_tail).  Every op
+    is per sample, so the denoised latents must equal those of the reference's two calls per step up to the convolution
+    library's choice of kernel for the other batch size; the cross-attention K/V of a merged pass come from the
+    per-sequence cache entry "both"."""
     from attention_interpolation_diffusion_b200.pipeline import InterpolationPipeline
     from attention_interpolation_diffusion_b200.unet_harness import build_unet
     net = build_unet("tiny", "cuda", torch.float16, seed=5)
@@ -750,14 +810,18 @@ def test_merged_plain_passes_equal_separate_passes(cabi):
                 negative_embeds=r(1, 77, 96), pooled_start=r(1, 1280), pooled_end=r(1, 1280), pooled_negative=r(1, 1280),
                 size=5, alpha=4.0, beta=4.0, num_inference_steps=6, warmup_ratio=0.5)
     outs = {}
-    for merge in (False, True):
-        for graphs in (False, True):
-            pipe = InterpolationPipeline(net, use_cuda_graphs=graphs, merge_plain_passes=merge)
-            pipe.load_aid(t=None, is_fused=True, atype="fused_outer", size=5, alpha=4, beta=4)
-            outs[merge, graphs] = pipe.interpolate(**args).float().cpu()
-            if merge:
-                kinds = {k[1] for k in pipe._graphs}
-                assert kinds == ({"cond", "uncond", "both"} if graphs else set()), kinds
-    assert torch.isfinite(outs[True, True]).all()
-    assert torch.equal(outs[True, True], outs[True, False])           # graph replay == eager
-    check(outs[True, False], outs[False, False], "merged vs separate passes", rel=2e-3)
+    for atype in ("fused_outer", "fused_inner"):
+        for merge, merge_aid in ((False, False), (True, False), (True, True)):
+            for graphs in (False, True):
+                pipe = InterpolationPipeline(net, use_cuda_graphs=graphs, merge_plain_passes=merge, merge_aid_passes=merge_aid)
+                pipe.load_aid(t=None, is_fused=True, atype=atype, size=5, alpha=4, beta=4)
+                outs[atype, merge, merge_aid, graphs] = pipe.interpolate(**args).float().cpu()
+                kinds = {(k[0], k[1]) for k in pipe._graphs}
+                want = {(True, "cond"), (False, "uncond")}
+                if merge:
+                    want = {(True, "both"), (False, "both")} if merge_aid else want | {(False, "both")}
+                assert kinds == (want if graphs else set()), kinds
+        for merge, merge_aid in ((True, False), (True, True)):
+            assert torch.isfinite(outs[atype, merge, merge_aid, True]).all()
+            assert torch.equal(outs[atype, merge, merge_aid, True], outs[atype, merge, merge_aid, False])   # graph replay == eager
+            check(outs[atype, merge, merge_aid, False], outs[atype, False, False, False], f"merged {merge_aid} vs separate passes ({atype})", rel=2e-3)

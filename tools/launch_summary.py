@@ -5,7 +5,9 @@ import csv
 import re
 import sys
 
-FAMILIES = [("paid::attn_tc_kernel", r"paid::.*attn_tc_kernel"), ("paid::linear_tc_pair_kernel (cta_group::2)", r"paid::.*linear_tc_pair"),
+FAMILIES = [("paid::attn_tc_kernel (outer)", r"paid::.*attn_tc_kernel"), ("paid::attn_dw_kernel (plain / inner)", r"paid::.*attn_dw_kernel"),
+            ("paid::linear_tc_pair_kernel, GEGLU epilogue (cta_group::2)", r"paid::.*linear_tc_pair_kernel<[^>]*\btrue\b|paid::.*linear_tc_pair_kernel<.*, true>"),
+            ("paid::linear_tc_pair_kernel (cta_group::2)", r"paid::.*linear_tc_pair"),
             ("paid::linear_tc_kernel", r"paid::.*linear_tc"), ("paid::geglu_kernel", r"paid::.*geglu"),
             ("paid::group_norm kernels", r"paid::.*gn_"), ("paid::add_layer_norm_kernel", r"paid::.*layer_norm"),
             ("paid:: other", r"paid::"), ("cuBLAS nvjet GEMM (FF, proj_in/out, embeddings)", r"nvjet"),
@@ -21,6 +23,8 @@ def main():
     rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
     hdr = rows[0]
     ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    first = next((i for i, r in enumerate(rows[1:], 1) if "paid::" in r[ik]), 1)   # drop the weight-initialisation kernels in front
+    rows = [hdr] + rows[first:]
     t, n = collections.Counter(), collections.Counter()
     for r in rows[1:]:
         v = float(r[iv].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}.get(r[iu], 1e-6)
