@@ -380,6 +380,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // All P.V products of this tile must have landed: a dedicated single-phase barrier (pv_done completes once
     // per step, and a parity wait cannot be used on a barrier whose phases this thread has skipped).
     ptx::mbar_wait(&bar->acc_final[t], 0);
+    // ... and pv_done has completed its last phase by now (committed just before acc_final by the same thread): observing
+    // it costs one successful poll and leaves no barrier phase unwaited at exit (compute-sanitizer synccheck "Missing wait")
+    ptx::mbar_wait(&bar->pv_done[t], (total_steps - 1) & 1);
     ptx::tc_fence_after();
     const float os = a.out_scale * (a.out_frame_scale ? a.out_frame_scale[n] : 1.f);
     const float cf[2] = {seg.a_active ? os * plan.wA / l_st[0] : 0.f, seg.b_active ? os * plan.wB / l_st[1] : 0.f};

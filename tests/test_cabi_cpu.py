@@ -185,3 +185,12 @@ def test_harness_block_restructure_equals_textbook_block():
         hh = hh + r.time_emb_proj(F.silu(temb))[:, :, None, None]
         hh = r.conv2(F.silu(r.norm2(hh)))
         assert torch.allclose(r(xi, temb), r.conv_shortcut(xi) + hh, atol=1e-5)
+
+
+def test_integration_stub_struct_matches_the_library(cabi):
+    """The ctypes struct a maintainer would copy out of INTEGRATION.md must be the struct the library validates
+    (struct_size guard): same fields, same types, same order as _cabi.PaidAttnParams."""
+    text = open(os.path.join(os.path.dirname(HEADER), "..", "INTEGRATION.md")).read()
+    block = text[text.index("class PaidAttnParams(ctypes.Structure)"):text.index("def outer_call")]
+    fields = re.findall(r'\("(\w+)",\s*ctypes\.(c_\w+)\)', block)
+    assert [(n, getattr(C, t)) for n, t in fields] == list(cabi.PaidAttnParams._fields_)

@@ -342,7 +342,7 @@ def test_pipeline_cuda_graph_replay_equals_eager(cabi):
     pipe = InterpolationPipeline(net, use_cuda_graphs=True)
     first = pipe.interpolate(**args)
     again = pipe.interpolate(**args)                       # second call: pure replays
-    assert pipe.graph_kernel_launches > 0 and len(pipe._graphs) == 3      # (AID, cond), (plain, uncond), (plain, both passes merged)
+    assert pipe.graph_kernel_launches > 0 and len(pipe._graphs) == 2      # (AID + guidance rows), (plain): both passes of a step in one call
     assert torch.equal(first, again)
     check(first.float().cpu(), eager.float().cpu(), "graph replay vs eager", rel=1e-3)
 
@@ -817,9 +817,10 @@ def test_merged_passes_equal_separate_passes(cabi):
                 pipe.load_aid(t=None, is_fused=True, atype=atype, size=5, alpha=4, beta=4)
                 outs[atype, merge, merge_aid, graphs] = pipe.interpolate(**args).float().cpu()
                 kinds = {(k[0], k[1]) for k in pipe._graphs}
-                want = {(True, "cond"), (False, "uncond")}
-                if merge:
-                    want = {(True, "both"), (False, "both")} if merge_aid else want | {(False, "both")}
+                if not merge:        # the reference's schedule: AID cond (warm-up), stock cond (afterwards), stock uncond (always)
+                    want = {(True, "cond"), (False, "cond"), (False, "uncond")}
+                else:
+                    want = {(True, "both"), (False, "both")} if merge_aid else {(True, "cond"), (False, "uncond"), (False, "both")}
                 assert kinds == (want if graphs else set()), kinds
         for merge, merge_aid in ((True, False), (True, True)):
             assert torch.isfinite(outs[atype, merge, merge_aid, True]).all()

@@ -6,7 +6,7 @@ import re
 import sys
 
 FAMILIES = [("paid::attn_tc_kernel (outer)", r"paid::.*attn_tc_kernel"), ("paid::attn_dw_kernel (plain / inner)", r"paid::.*attn_dw_kernel"),
-            ("paid::linear_tc_pair_kernel, GEGLU epilogue (cta_group::2)", r"paid::.*linear_tc_pair_kernel<[^>]*\btrue\b|paid::.*linear_tc_pair_kernel<.*, true>"),
+            ("paid::linear_tc_pair_kernel, GEGLU epilogue (cta_group::2)", r"paid::.*linear_tc_pair_kernel<[^>,]*, *(\(bool\))?(1|true)>"),
             ("paid::linear_tc_pair_kernel (cta_group::2)", r"paid::.*linear_tc_pair"),
             ("paid::linear_tc_kernel", r"paid::.*linear_tc"), ("paid::geglu_kernel", r"paid::.*geglu"),
             ("paid::group_norm kernels", r"paid::.*gn_"), ("paid::add_layer_norm_kernel", r"paid::.*layer_norm"),
