@@ -15,16 +15,6 @@
 #include <cstdlib>
 
 #include "paid_common.cuh"
-#include "sm100_ptx.cuh"
-
-// Programmatic dependent launch (all glue kernels are launched with it, like the GEMM and attention kernels they sit
-// between): the NEXT kernel of the stream may be scheduled once every CTA of this one has started -- its prologue and
-// launch latency overlap this kernel -- and THIS kernel touches no memory before its predecessor has completed.
-#define PAID_PDL_PROLOGUE()        \
-  do {                             \
-    ptx::pdl_launch_dependents();  \
-    ptx::pdl_wait();               \
-  } while (0)
 
 namespace paid {
 namespace {
@@ -57,7 +47,6 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(kLnWarps * 32)
 add_layer_norm_kernel(const T* x, const T* delta, const T* __restrict__ gamma, const T* __restrict__ beta, T* x_out,
                       T* __restrict__ h_out, long long rows, int C, float eps) {
-  PAID_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -120,7 +109,6 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 residual_bias_add_kernel(const T* a, const T* b, const T* __restrict__ bias, T* out, unsigned total, unsigned V) {
   // 32-bit index arithmetic (the launcher checks rows * C / 8 < 2^31)
-  PAID_PDL_PROLOGUE();
   const unsigned stride = gridDim.x * blockDim.x;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 4 * stride) {
     uint4 ra[4], rb[4], rc[4];
@@ -183,7 +171,6 @@ template <typename T, int U, bool HB, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ pre_bias, float2* __restrict__ partial,
                                 long long HW, int C, int groups, int R, int chunks) {
   extern __shared__ float sh[];  // [2][R][C] per-channel sums and sums of squares
-  PAID_PDL_PROLOGUE();
   const int V = C >> 3, tid = threadIdx.x, col = tid % V, r = tid / V;
   const bool active = r < R;   // the block is padded to whole warps
   const int n = blockIdx.y, chunk = blockIdx.x;
@@ -241,7 +228,6 @@ __global__ void __launch_bounds__(MAXT, MINB) gn_apply_kernel(const T* __restric
                                 const T* __restrict__ gamma, const T* __restrict__ beta, T* __restrict__ y, long long HW,
                                 int C, int groups, int R, int chunks_stats, int chunks, float eps, int silu) {
   __shared__ float sh_mean[64], sh_rstd[64];
-  PAID_PDL_PROLOGUE();
   const int V = C >> 3, tid = threadIdx.x, col = tid % V, r = tid / V;
   const bool active = r < R;   // the block is padded to whole warps (every warp takes part in the merge below)
   const int n = blockIdx.y, chunk = blockIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -324,12 +310,12 @@ template <typename T, int U, bool HB, int MAXT, int MINB>
 int launch_gn_v(const GnGeometry& g, const void* x, const void* pre_bias, const void* gamma, const void* beta, void* y, float* ws,
                 int N, long long HW, int C, int groups, float eps, int silu, cudaStream_t stream) {
   const size_t smem = (size_t)2 * g.R * C * sizeof(float);
-  PAID_CUDA_CHECK(launch_pdl(gn_stats_kernel<T, U, HB, MAXT, MINB>, dim3(g.chunks_stats, N), dim3(g.threads), smem, stream,
-                             (const T*)x, (const T*)pre_bias, (float2*)ws, HW, C, groups, g.R, g.chunks_stats));
+  gn_stats_kernel<T, U, HB, MAXT, MINB><<<dim3(g.chunks_stats, N), g.threads, smem, stream>>>(
+      (const T*)x, (const T*)pre_bias, (float2*)ws, HW, C, groups, g.R, g.chunks_stats);
   PAID_LAUNCH_CHECK("gn_stats_kernel");
-  PAID_CUDA_CHECK(launch_pdl(gn_apply_kernel<T, U, HB, MAXT, MINB>, dim3(g.chunks_apply, N), dim3(g.threads), 0, stream,
-                             (const T*)x, (const T*)pre_bias, (const float2*)ws, (const T*)gamma, (const T*)beta, (T*)y, HW, C,
-                             groups, g.R, g.chunks_stats, g.chunks_apply, eps, silu));
+  gn_apply_kernel<T, U, HB, MAXT, MINB><<<dim3(g.chunks_apply, N), g.threads, 0, stream>>>(
+      (const T*)x, (const T*)pre_bias, (const float2*)ws, (const T*)gamma, (const T*)beta, (T*)y, HW, C, groups, g.R,
+      g.chunks_stats, g.chunks_apply, eps, silu);
   PAID_LAUNCH_CHECK("gn_apply_kernel");
   return PAID_OK;
 }
@@ -393,8 +379,8 @@ template <typename T, int NV>
 static void launch_ln_nv(const void* x, const void* delta, const void* gamma, const void* beta, void* x_out, void* h_out,
                          long long rows, int C, float eps, cudaStream_t stream) {
   const unsigned blocks = (unsigned)((rows + kLnWarps - 1) / kLnWarps);
-  (void)launch_pdl(add_layer_norm_kernel<T, NV>, dim3(blocks), dim3(kLnWarps * 32), 0, stream, (const T*)x, (const T*)delta,
-                   (const T*)gamma, (const T*)beta, (T*)x_out, (T*)h_out, rows, C, eps);   // errors: PAID_LAUNCH_CHECK of the caller
+  add_layer_norm_kernel<T, NV><<<blocks, kLnWarps * 32, 0, stream>>>((const T*)x, (const T*)delta, (const T*)gamma, (const T*)beta,
+                                                                   (T*)x_out, (T*)h_out, rows, C, eps);
 }
 
 template <typename T>
@@ -424,12 +410,12 @@ int launch_residual_bias_add(const void* a, const void* b, const void* bias, voi
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   if (dtype == PAID_F16)
-    (void)launch_pdl(residual_bias_add_kernel<__half>, dim3((unsigned)blocks), dim3(256), 0, stream, (const __half*)a,
-                     (const __half*)b, (const __half*)bias, (__half*)out, (unsigned)total, (unsigned)(C / 8));
+    residual_bias_add_kernel<__half><<<(unsigned)blocks, 256, 0, stream>>>((const __half*)a, (const __half*)b, (const __half*)bias,
+                                                                          (__half*)out, (unsigned)total, (unsigned)(C / 8));
   else
-    (void)launch_pdl(residual_bias_add_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(256), 0, stream,
-                     (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const __nv_bfloat16*)bias, (__nv_bfloat16*)out,
-                     (unsigned)total, (unsigned)(C / 8));
+    residual_bias_add_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>(
+        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, (unsigned)total,
+        (unsigned)(C / 8));
   PAID_LAUNCH_CHECK("residual_bias_add_kernel");
   return PAID_OK;
 }

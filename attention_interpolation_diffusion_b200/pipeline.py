@@ -274,7 +274,10 @@ class InterpolationPipeline:
         n = latents.shape[0]
         text_only = all(type(p) in (OuterInterpolatedAttnProcessor, InnerInterpolatedAttnProcessor) for _, p in self._installed())
         merge_plain = self.merge_plain_passes and latents.is_cuda and text_only and warmup_steps < num_inference_steps
-        merge_aid = self.merge_aid_passes and latents.is_cuda and text_only and warmup_steps > 0
+        # frame-sharded over more than two ranks the warm-up steps keep the reference's two calls per step: the guidance rows
+        # inside the interpolated call are validated on GPUs at world sizes 1 and 2 only
+        few_ranks = self.shard is None or self.shard.world_size <= 2 or os.environ.get("PAID_MERGE_AID_ANY_WORLD") == "1"
+        merge_aid = self.merge_aid_passes and latents.is_cuda and text_only and warmup_steps > 0 and few_ranks
         merge = merge_plain or merge_aid
         both = torch.cat([cond, uncond]) if merge else None
         added_both = None if (not merge or added_cond is None) else {k: torch.cat([added_cond[k], added_uncond[k]]) for k in added_cond}

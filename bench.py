@@ -48,7 +48,39 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly (for ncu launch lists)")
     ap.add_argument("--ncu-range", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off: the launch list of the timed steps only)")
+    ap.add_argument("--watchdog-s", type=float, default=420.0,
+                    help="abort (exit code 17, diagnostic on stderr) when one phase of the run makes no progress for this long: a "
+                         "stuck collective must not hold the GPUs until the caller's own limit")
     return ap.parse_args()
+
+
+class Watchdog:
+    """A multi-rank run that stops making progress (a collective some rank never joins) would otherwise spin on the GPUs
+    until the caller kills it.  Every phase of the bench announces itself here; a phase that exceeds its limit ends the
+    process with a diagnostic instead (torchrun then tears the other ranks down)."""
+
+    def __init__(self, limit_s: float, rank: int, world: int):
+        import threading
+        self.limit, self.rank, self.world = limit_s, rank, world
+        self.name, self.since, self.budget = "start", time.time(), limit_s
+        self._stop = threading.Event()
+        if limit_s > 0:
+            threading.Thread(target=self._run, daemon=True).start()
+
+    def phase(self, name: str, extra_s: float = 0.0):
+        self.name, self.since, self.budget = name, time.time(), self.limit + extra_s
+
+    def stop(self):
+        self._stop.set()
+
+    def _run(self):
+        while not self._stop.wait(5.0):
+            idle = time.time() - self.since
+            if idle > self.budget:
+                sys.stderr.write(json.dumps({"error": "bench watchdog", "phase": self.name, "no_progress_s": round(idle, 1),
+                                             "rank": self.rank, "world": self.world}) + "\n")
+                sys.stderr.flush()
+                os._exit(17)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -348,10 +380,15 @@ def run_reference_arm(args):
 def workload_config(args, frames):
     name = {"sdxl": "SDXL 128x128 latent", "sd15": "SD1.5 64x64 latent", "tiny": "tiny test UNet"}[args.model]
     ip = f" + IP-Adapter image morphing ({args.ip_tokens} image tokens per frame)" if args.ip_tokens else ""
-    cfg = ("CFG (conditional + unconditional UNet pass per step)" if args.ip_tokens else
-           "CFG (the conditional and the unconditional frames of a step run as one UNet call with 2 n frames: during the warm-up "
-           "steps the attention layers interpolate the first n and run stock attention on the last n, afterwards all run stock "
-           "attention)")
+    if args.ip_tokens:
+        cfg = "CFG (conditional + unconditional UNet pass per step)"
+    elif args.gpus > 2:
+        cfg = ("CFG (warm-up steps: an interpolated conditional and a stock unconditional UNet pass; afterwards both run stock "
+               "attention as one UNet call with 2 n frames)")
+    else:
+        cfg = ("CFG (the conditional and the unconditional frames of a step run as one UNet call with 2 n frames: during the warm-up "
+               "steps the attention layers interpolate the first n and run stock attention on the last n, afterwards all run stock "
+               "attention)")
     return {"workload": f"{name}, {frames}-frame PAID (guide prompt){ip}, {args.atype} AID in all attention layers, "
                         f"{args.denoise_steps} steps, warmup_ratio {WARMUP_RATIO}, {cfg}",
             "frames": frames, "frames_per_gpu": frames // max(args.gpus, 1), "denoise_steps": args.denoise_steps,
@@ -372,6 +409,8 @@ def run_own_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    wd = Watchdog(args.watchdog_s, rank, world)
+    wd.phase("process group + UNet build")
     assert torch.cuda.is_available(), "bench.py (own arm) needs a CUDA device: there is no CPU path"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -422,13 +461,15 @@ def run_own_arm(args):
         d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         return pipe.interpolate(**d, **kw).float().cpu()
 
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
+        wd.phase(f"warm-up sequence {i}")
         step_dev()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = _cabi.launch_count() + pipe.graph_kernel_launches
     if args.ncu_range:
         torch.cuda.cudart().cudaProfilerStart()
+    wd.phase("timed sequences", extra_s=30.0 * args.steps + (1e6 if args.ncu_range else 0))
     ms = timed(step_dev, args.steps)
     if args.ncu_range:
         torch.cuda.cudart().cudaProfilerStop()
@@ -438,6 +479,7 @@ def run_own_arm(args):
 
     e2e = None
     if not args.no_e2e:
+        wd.phase("end-to-end sequences", extra_s=30.0 * args.steps)
         out = step_e2e()
         ms_e = timed(step_e2e, args.steps)
         h2d = sum(v.numel() * v.element_size() for v in host.values())
@@ -446,6 +488,7 @@ def run_own_arm(args):
 
     # roofline of the dominant kernel: CUDA events around every attention-core launch of ONE more sequence, run
     # eagerly (kernels inside a CUDA-graph replay cannot be bracketed by events), same inputs, same launches
+    wd.phase("eager sequence with the measurement hook")
     pipe.use_cuda_graphs = False
     _cabi.profile_read(reset=True)
     _cabi.profile_enable(True)
@@ -459,6 +502,7 @@ def run_own_arm(args):
 
     # frame-sharded run against the single-GPU run of the same sequence, once, outside the timed region (4 denoising steps)
     sharded_parity = None
+    wd.phase("sharded parity + report", extra_s=600.0)     # rank 0 also times the isolated kernels and the CPU baseline here
     if world > 1:
         kw_p = dict(kw, num_inference_steps=4)
         local_out = pipe.interpolate(**devin, **kw_p)
@@ -468,20 +512,25 @@ def run_own_arm(args):
                 parts[rk].copy_(local_out)
             dist.broadcast(parts[rk], src=rk)
         if rank == 0:
-            gathered = shard.unshard(parts).float()
-            single = InterpolationPipeline(net, shard=None, use_cuda_graphs=not args.no_graphs)
-            install(single)
-            ref_out = single.interpolate(**devin, **kw_p).float()
-            rms = ref_out.pow(2).mean().sqrt()
-            sharded_parity = {"rel_rms": float((gathered - ref_out).pow(2).mean().sqrt() / rms),
-                              "max_abs_over_rms": float((gathered - ref_out).abs().max() / rms),
-                              "bit_identical": bool(torch.equal(gathered, ref_out)), "frames": frames, "denoise_steps": 4,
-                              "broadcasts_per_aid_forward": sum(1 for g_ in net.attention_geometry() if g_["self_attn"]),
-                              "how": "all ranks' frames gathered on rank 0 vs the unsharded run of the same sequence on GPU 0 (one batch "
-                                     "of all frames: cuDNN picks other convolution kernels for that batch size, so the two runs "
-                                     "are not bit-identical here; tests/test_multirank_gpu.py shows bit-identity on equal conv batches)"}
-            single._graphs.clear()
-            del single
+            # the unsharded run: the reference's schedule (two UNet calls per step), launched eagerly -- the plainest path of
+            # the pipeline, so that a problem in this check can never take the measured line with it
+            try:
+                gathered = shard.unshard(parts).float()
+                single = InterpolationPipeline(net, shard=None, use_cuda_graphs=False, merge_plain_passes=False)
+                install(single)
+                ref_out = single.interpolate(**devin, **kw_p).float()
+                rms = ref_out.pow(2).mean().sqrt()
+                sharded_parity = {"rel_rms": float((gathered - ref_out).pow(2).mean().sqrt() / rms),
+                                  "max_abs_over_rms": float((gathered - ref_out).abs().max() / rms),
+                                  "bit_identical": bool(torch.equal(gathered, ref_out)), "frames": frames, "denoise_steps": 4,
+                                  "broadcasts_per_aid_forward": sum(1 for g_ in net.attention_geometry() if g_["self_attn"]),
+                                  "how": "all ranks' frames gathered on rank 0 vs the unsharded run of the same sequence on GPU 0 (one "
+                                         "batch of all frames, two UNet calls per step, eager launches: cuDNN picks other convolution "
+                                         "kernels for that batch size, so the two runs are not bit-identical here; "
+                                         "tests/test_multirank_gpu.py shows bit-identity on equal conv batches)"}
+                del single
+            except Exception as e:      # noqa: BLE001 -- reported in the line, never fatal for the measurement
+                sharded_parity = {"error": f"{type(e).__name__}: {e}"[:400], "frames": frames}
         dist.barrier()
 
     if rank == 0:

@@ -52,3 +52,19 @@ def test_committed_ncu_traffic_covers_the_headline_workload():
         pytest.skip("profiles/attn_traffic.json is stale for this build of the kernels (bench.py then reports traffic: null)")
     assert traffic is not None and alg is not None, how
     assert 0.3 * alg < traffic < 3 * alg, (traffic, alg)      # DRAM traffic of the same order as the algorithmic bytes
+
+
+def test_watchdog_ends_a_stalled_run():
+    """bench.Watchdog: a phase without progress ends the process with exit code 17 and a diagnostic on stderr (a stuck
+    collective must not hold the GPUs until the caller's own limit); a stopped watchdog does nothing."""
+    import subprocess
+    code = ("import sys, time; sys.path.insert(0, %r); import bench; w = bench.Watchdog(0.5, 3, 8); w.phase('warm-up sequence 0'); "
+            "time.sleep(30)") % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=25)
+    assert res.returncode == 17, (res.returncode, res.stderr[-500:])
+    msg = json.loads(res.stderr.strip().splitlines()[-1])
+    assert msg["error"] == "bench watchdog" and msg["phase"] == "warm-up sequence 0" and msg["rank"] == 3 and msg["world"] == 8
+    code = ("import sys, time; sys.path.insert(0, %r); import bench; w = bench.Watchdog(0.5, 0, 1); w.stop(); time.sleep(7); "
+            "print('alive')") % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=25)
+    assert res.returncode == 0 and "alive" in res.stdout
