@@ -80,7 +80,12 @@ class Watchdog:
                 sys.stderr.write(json.dumps({"error": "bench watchdog", "phase": self.name, "no_progress_s": round(idle, 1),
                                              "rank": self.rank, "world": self.world}) + "\n")
                 sys.stderr.flush()
-                os._exit(17)
+                try:                                  # where every thread of this rank stands (the next session's first clue)
+                    import faulthandler
+                    faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+                    sys.stderr.flush()
+                finally:
+                    os._exit(17)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -465,7 +470,8 @@ def run_own_arm(args):
         wd.phase(f"warm-up sequence {i}")
         step_dev()
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:           # one nvidia-smi poller per job (rank 0's GPU), not one per rank
+        sampler.start()
     launches0 = _cabi.launch_count() + pipe.graph_kernel_launches
     if args.ncu_range:
         torch.cuda.cudart().cudaProfilerStart()

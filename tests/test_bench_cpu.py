@@ -62,7 +62,8 @@ def test_watchdog_ends_a_stalled_run():
             "time.sleep(30)") % ROOT
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=25)
     assert res.returncode == 17, (res.returncode, res.stderr[-500:])
-    msg = json.loads(res.stderr.strip().splitlines()[-1])
+    msg = json.loads(next(l for l in res.stderr.splitlines() if l.startswith('{')))      # followed by the threads' stack dump
+    assert "Thread" in res.stderr or "File" in res.stderr
     assert msg["error"] == "bench watchdog" and msg["phase"] == "warm-up sequence 0" and msg["rank"] == 3 and msg["world"] == 8
     code = ("import sys, time; sys.path.insert(0, %r); import bench; w = bench.Watchdog(0.5, 0, 1); w.stop(); time.sleep(7); "
             "print('alive')") % ROOT
