@@ -295,6 +295,8 @@ class InterpolationPipeline:
                 noise_uncond = self._forward(False, "uncond", model_in, t, uncond, added_uncond, graphs)
             noise = noise_uncond + guidance_scale * (noise_text - noise_uncond)
             latents = self.scheduler.step(noise, t, latents)
+        for _, proc in self._installed():
+            proc.cfg_tail = 0               # processors called outside the step loop see plain interpolation batches again
         return latents
 
     def _set_mode(self, aid: bool, tail: int = 0):
