@@ -67,6 +67,14 @@ def test_argument_errors_are_reported_not_thrown(cabi):
     p.L = 77                                                                 # self-attention needs L == S
     assert lib.paid_attn_forward(C.byref(p), None) == cabi.PAID_EINVAL
     assert lib.paid_attn_forward(None, None) == cabi.PAID_EINVAL
+    # guidance rows (plain_tail) need per-frame K / V: one shared (L, C) matrix cannot serve the interpolated frames
+    p.L, p.mode = 64, 0
+    buf = torch.zeros(16, dtype=torch.float16)          # validation runs before anything touches the pointers
+    p.x = p.wq = p.wo = p.y = p.k_pre = p.v_pre = buf.data_ptr()
+    p.kv_pre_broadcast, p.plain_tail = 1, 3
+    assert lib.paid_attn_forward(C.byref(p), None) == cabi.PAID_EINVAL and "plain_tail" in cabi.last_error()
+    with pytest.raises(ValueError, match="plain_tail"):
+        cabi.make_params(torch.zeros(3, 8, 64, dtype=torch.float16), None, None, None, None, None, None, None, 1, 1, True, plain_tail=3)
     assert lib.paid_linear(None, None, None, None, 1, 1, 1, 0, 0, None) == cabi.PAID_EINVAL
     c = cabi.PaidCoreParams()
     assert lib.paid_attn_core(C.byref(c), None) == cabi.PAID_EINVAL
