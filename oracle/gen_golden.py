@@ -207,7 +207,30 @@ def main_ip():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **blob)
 
 
+def main_slerp():
+    """Latent interpolation used to build the frames (reference interpolation.py:861-918): generic rows, a colinear pair
+    (falls back to lerp, :887-900) and an all-zero row (NaN cosine, same fallback), fp64."""
+    ref = sys.modules["interpolation"]
+    g = torch.Generator("cpu").manual_seed(404)
+    a = torch.randn(1, 4, 8, 8, generator=g, dtype=torch.float64)
+    b = torch.randn(1, 4, 8, 8, generator=g, dtype=torch.float64)
+    b[0, 1, 2] = 1.7 * a[0, 1, 2]          # a colinear row
+    a[0, 3, 5] = 0                         # a zero row
+    ts = [0.0, 0.1, 0.35, 0.5, 0.9, 1.0]
+    out = torch.stack([ref.slerp(a, b, t) for t in ts])
+    for i, t in enumerate(ts):
+        err = (O.slerp(a, b, t) - out[i]).abs().max().item()
+        assert err < 1e-12, (t, err)
+    np.savez_compressed(os.path.join(OUT, "aux_slerp.npz"), a=a.numpy(), b=b.numpy(), ts=np.array(ts), out=out.numpy())
+    print("slerp: oracle == reference on", len(ts), "parameters")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
+    if "--only-slerp" in sys.argv:          # adds tests/golden/aux_slerp.npz without rewriting the attention vectors
+        import_reference()
+        main_slerp()
+        sys.exit(0)
     main()
     main_ip()
+    main_slerp()

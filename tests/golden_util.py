@@ -13,7 +13,7 @@ MODES = [("outer", False), ("outer", True), ("inner", False), ("inner", True)]
 
 def case_names():
     return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-                  if not n.startswith(("ip_", "e2e_")))
+                  if not n.startswith(("ip_", "e2e_", "aux_")))      # aux_: vectors of helpers next to the path (slerp)
 
 
 def ip_case_names():

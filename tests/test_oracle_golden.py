@@ -75,3 +75,17 @@ def test_slerp_matches_definition():
     a, b = torch.randn(1, 4, 8, 8, dtype=torch.float64), torch.randn(1, 4, 8, 8, dtype=torch.float64)
     assert torch.allclose(O.slerp(a, b, 0.0), a) and torch.allclose(O.slerp(a, b, 1.0), b)
     assert torch.allclose(O.slerp(a, a * 2, 0.25), torch.lerp(a, a * 2, 0.25))  # colinear -> lerp
+
+
+def test_slerp_matches_the_reference(golden_dir):
+    """tests/golden/aux_slerp.npz: outputs of the unmodified reference slerp (interpolation.py:861-918; generic rows, a colinear
+    row and an all-zero row) -- the oracle's restatement and the pipeline's own must reproduce them."""
+    import os
+
+    import numpy as np
+    from attention_interpolation_diffusion_b200.pipeline import slerp
+    blob = np.load(os.path.join(golden_dir, "aux_slerp.npz"))
+    a, b, out = (torch.from_numpy(blob[k]) for k in ("a", "b", "out"))
+    for i, t in enumerate(blob["ts"].tolist()):
+        assert (O.slerp(a, b, t) - out[i]).abs().max() < 1e-12, t
+        assert (slerp(a, b, t) - out[i]).abs().max() < 1e-12, t
